@@ -1,0 +1,198 @@
+/*
+ * grayskull.h -- drop-in boundary header for the B200-native hot path.
+ *
+ * The reference library (zserge/grayskull) has no plugin registry: its boundary IS its
+ * single header, every public function being declared GS_API (reference grayskull.h:7-9).
+ * This header keeps that boundary -- the gs_* names, by-value `struct gs_image {w,h,data}`
+ * arguments, and the error convention (gs_assert -> message + abort) -- and rebinds the
+ * stencil / sliding-window hot path to libgrayskull_b200.so (hand-written sm_100a CUDA).
+ *
+ * Two ways to use it:
+ *
+ *  1. Overlay mode (what a maintainer of the reference would do): compile with
+ *       -DGS_UPSTREAM_HEADER='"/path/to/upstream/grayskull.h"'
+ *     The upstream header is included unchanged; its hot-path definitions are renamed
+ *     gs_cpu_<op> (still callable, handy for A/B checks) and the gs_<op> names resolve to the
+ *     extern "C" entry points below.  Everything outside the hot path (crop, threshold,
+ *     blobs, contours, template matching, PGM I/O ...) stays the upstream CPU code, so
+ *     test.c and examples/nanomagick/nanomagick.c build unmodified.
+ *
+ *  2. Stand-alone mode (no upstream tree available): this header provides the types, the
+ *     inline helpers callers use directly (gs_valid/gs_get/gs_set/gs_for/gs_integral_sum,
+ *     GS_MIN/GS_MAX, gs_assert, gs_alloc/gs_free) and the hot-path prototypes only.
+ *
+ * Each prototype cites the reference definition it replaces (file:line in the reference).
+ * Host code stays C99; the shim is a plain C ABI (pointers, sizes, PODs).
+ */
+#ifndef GRAYSKULL_B200_DROPIN_H
+#define GRAYSKULL_B200_DROPIN_H
+
+#ifdef GS_UPSTREAM_HEADER
+/* ---- overlay mode ------------------------------------------------------------------- */
+#define gs_blur gs_cpu_blur
+#define gs_sobel gs_cpu_sobel
+#define gs_erode gs_cpu_erode
+#define gs_dilate gs_cpu_dilate
+#define gs_adaptive_threshold gs_cpu_adaptive_threshold
+#define gs_resize gs_cpu_resize
+#define gs_downsample gs_cpu_downsample
+#define gs_integral gs_cpu_integral
+#define gs_fast gs_cpu_fast
+#define gs_compute_orientation gs_cpu_compute_orientation
+#define gs_brief_descriptor gs_cpu_brief_descriptor
+#define gs_orb_extract gs_cpu_orb_extract
+#define gs_lbp_window gs_cpu_lbp_window
+#define gs_lbp_detect gs_cpu_lbp_detect
+#include GS_UPSTREAM_HEADER
+#undef gs_blur
+#undef gs_sobel
+#undef gs_erode
+#undef gs_dilate
+#undef gs_adaptive_threshold
+#undef gs_resize
+#undef gs_downsample
+#undef gs_integral
+#undef gs_fast
+#undef gs_compute_orientation
+#undef gs_brief_descriptor
+#undef gs_orb_extract
+#undef gs_lbp_window
+#undef gs_lbp_detect
+
+#else
+/* ---- stand-alone mode --------------------------------------------------------------- */
+#include <limits.h>
+#include <stdint.h>
+
+#ifndef GS_NO_STDLIB
+#include <stdio.h>
+#include <stdlib.h>
+#endif
+
+#define GS_MIN(a, b) ((a) < (b) ? (a) : (b))
+#define GS_MAX(a, b) ((a) > (b) ? (a) : (b))
+
+/* Layouts are ABI: they must match the reference byte for byte (grayskull.h:14-64). */
+struct gs_image {
+  unsigned w, h;
+  uint8_t *data;
+};
+struct gs_rect {
+  unsigned x, y, w, h;
+};
+struct gs_point {
+  unsigned x, y;
+};
+struct gs_keypoint {
+  struct gs_point pt;
+  unsigned response;
+  float angle;
+  uint32_t descriptor[8];
+};
+struct gs_lbp_cascade {
+  uint16_t window_w, window_h;
+  uint16_t nfeatures, nweaks, nstages;
+  const int8_t *features;           /* nfeatures x {x, y, w, h} of one LBP cell */
+  const uint16_t *weak_feature_idx; /* per weak classifier */
+  const float *weak_left_val, *weak_right_val;
+  const uint16_t *weak_subset_offset, *weak_num_subsets;
+  const int32_t *subsets;           /* 256-bit LUT per weak (8 words) */
+  const uint16_t *stage_weak_start, *stage_nweaks;
+  const float *stage_threshold;
+};
+
+static inline int gs_valid(struct gs_image img) { return img.data && img.w > 0 && img.h > 0; }
+
+#ifdef GS_NO_STDLIB
+#define gs_assert(cond)
+#else
+#define gs_assert(cond)                               \
+  if (!(cond)) {                                      \
+    fprintf(stderr, "Assertion failed: %s\n", #cond); \
+    abort();                                          \
+  }
+/* zero-filled, like the reference (callers rely on it for the sobel border and the FAST
+ * score-map ring, e.g. nanomagick.c:139-140,228-229) */
+static inline struct gs_image gs_alloc(unsigned w, unsigned h) {
+  struct gs_image img = {0, 0, NULL};
+  if (w == 0 || h == 0) return img;
+  img.data = (uint8_t *)calloc((size_t)w * h, 1);
+  if (img.data) img.w = w, img.h = h;
+  return img;
+}
+static inline void gs_free(struct gs_image img) { free(img.data); }
+#endif
+
+#define gs_for(img, x, y)                \
+  for (unsigned y = 0; y < (img).h; y++) \
+    for (unsigned x = 0; x < (img).w; x++)
+
+/* out-of-bounds read -> 0, out-of-bounds write -> dropped (reference grayskull.h:143-148) */
+static inline uint8_t gs_get(struct gs_image img, unsigned x, unsigned y) {
+  return (gs_valid(img) && x < img.w && y < img.h) ? img.data[y * img.w + x] : 0;
+}
+static inline void gs_set(struct gs_image img, unsigned x, unsigned y, uint8_t value) {
+  if (gs_valid(img) && x < img.w && y < img.h) img.data[y * img.w + x] = value;
+}
+
+/* inclusive box sum over [x, x+w-1] x [y, y+h-1] of a gs_integral table (grayskull.h:754-763) */
+static inline uint32_t gs_integral_sum(const unsigned *ii, unsigned iw, unsigned x, unsigned y,
+                                       unsigned w, unsigned h) {
+  unsigned xr = x + w - 1, yb = y + h - 1;
+  unsigned above_left = (x && y) ? ii[(y - 1) * iw + (x - 1)] : 0;
+  unsigned above = y ? ii[(y - 1) * iw + xr] : 0;
+  unsigned left = x ? ii[yb * iw + (x - 1)] : 0;
+  gs_assert(ii && iw > 0 && x + w <= iw);
+  return ii[yb * iw + xr] + above_left - above - left;
+}
+#endif /* GS_UPSTREAM_HEADER */
+
+/* ---- the hot path: extern "C" entry points of libgrayskull_b200.so -------------------- */
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Pointer kinds: every image / table pointer may be device, managed or plain host memory.
+ * Device and managed pointers run in place; host pointers are staged through the library's
+ * device workspace (correct, PCIe-bound).  All calls below are synchronous: on return the
+ * results are visible through the pointers that were passed in.  dst/src aliasing is not
+ * supported for the stencil ops (no reference caller does it either). */
+
+/* box mean over the border-clipped (2r+1)^2 window, sum / count -- grayskull.h:268-283 */
+void gs_blur(struct gs_image dst, struct gs_image src, unsigned radius);
+/* 3x3 Sobel, (|gx|+|gy|)/2 clamped, interior only, dst border untouched -- grayskull.h:306-320 */
+void gs_sobel(struct gs_image dst, struct gs_image src);
+/* 3x3 min / max over in-bounds neighbours -- grayskull.h:285-304 */
+void gs_erode(struct gs_image dst, struct gs_image src);
+void gs_dilate(struct gs_image dst, struct gs_image src);
+/* src > clipped-box-mean - c ? 255 : 0 -- grayskull.h:230-247 */
+void gs_adaptive_threshold(struct gs_image dst, struct gs_image src, unsigned radius, int c);
+/* pixel-centre bilinear resize, fp32 evaluation order preserved -- grayskull.h:171-187 */
+void gs_resize(struct gs_image dst, struct gs_image src);
+/* 2x2 mean, dst must be src/2 -- grayskull.h:189-197 */
+void gs_downsample(struct gs_image dst, struct gs_image src);
+/* inclusive u32 summed-area table, w*h entries -- grayskull.h:744-752 */
+void gs_integral(struct gs_image src, unsigned *ii);
+/* FAST-9 score map + 3x3 NMS, raster-ordered keypoints capped at nkps -- grayskull.h:482-534 */
+unsigned gs_fast(struct gs_image img, struct gs_image scoremap, struct gs_keypoint *kps,
+                 unsigned nkps, unsigned threshold);
+/* intensity-centroid angle over the radius-r disc -- grayskull.h:608-621 */
+float gs_compute_orientation(struct gs_image img, unsigned x, unsigned y, unsigned r);
+/* rotated BRIEF-256 of one keypoint (kp->pt, kp->angle in; kp->descriptor out) -- :623-637 */
+void gs_brief_descriptor(struct gs_image img, struct gs_keypoint *kp);
+/* FAST -> stable sort by response -> 15 px margin filter -> angle + BRIEF -- grayskull.h:651-669 */
+unsigned gs_orb_extract(struct gs_image img, struct gs_keypoint *kps, unsigned nkps,
+                        unsigned threshold, uint8_t *scoremap_buffer);
+/* one cascade window -- grayskull.h:790-813 */
+unsigned gs_lbp_window(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw,
+                       unsigned ih, int x, int y, float scale);
+/* multi-scale sliding window, (scale, y, x)-ordered rects capped at max_rects -- :815-835 */
+unsigned gs_lbp_detect(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw,
+                       unsigned ih, struct gs_rect *rects, unsigned max_rects,
+                       float scale_factor, float min_scale, float max_scale, int step);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GRAYSKULL_B200_DROPIN_H */

@@ -1,0 +1,181 @@
+"""ctypes loaders shared by the tests: the oracle restatement, the real reference build
+(oracle/_ref, when present) and synthetic-input generators.  TEST INFRASTRUCTURE only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+class Image(C.Structure):
+    _fields_ = [("w", C.c_uint), ("h", C.c_uint), ("data", C.c_void_p)]
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("response", C.c_uint), ("angle", C.c_float),
+                ("descriptor", C.c_uint32 * 8)]
+
+
+class Rect(C.Structure):
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("w", C.c_uint), ("h", C.c_uint)]
+
+
+class Cascade(C.Structure):
+    _fields_ = [
+        ("window_w", C.c_uint16), ("window_h", C.c_uint16),
+        ("nfeatures", C.c_uint16), ("nweaks", C.c_uint16), ("nstages", C.c_uint16),
+        ("features", C.c_void_p), ("weak_feature_idx", C.c_void_p),
+        ("weak_left_val", C.c_void_p), ("weak_right_val", C.c_void_p),
+        ("weak_subset_offset", C.c_void_p), ("weak_num_subsets", C.c_void_p),
+        ("subsets", C.c_void_p), ("stage_weak_start", C.c_void_p), ("stage_nweaks", C.c_void_p),
+        ("stage_threshold", C.c_void_p),
+    ]
+
+
+KP_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("response", "<u4"), ("angle", "<f4"),
+                     ("descriptor", "<u4", (8,))])
+RECT_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("w", "<u4"), ("h", "<u4")])
+assert KP_DTYPE.itemsize == 48 and RECT_DTYPE.itemsize == 16 and C.sizeof(Cascade) == 96
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def img(a):
+    """numpy (h, w) uint8 array -> struct gs_image by value"""
+    assert a.dtype == np.uint8 and a.flags.c_contiguous
+    return Image(a.shape[1], a.shape[0], a.ctypes.data)
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "all"], check=True)
+
+
+_cache = {}
+
+
+def oracle():
+    """our C restatement (oracle/libgs_oracle.so)"""
+    if "o" not in _cache:
+        path = os.path.join(ORACLE_DIR, "libgs_oracle.so")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(
+                os.path.join(ORACLE_DIR, "gs_oracle.c")):
+            build_oracle()
+        lib = C.CDLL(path)
+        lib.gso_fast.restype = C.c_uint
+        lib.gso_orb_extract.restype = C.c_uint
+        lib.gso_lbp_window.restype = C.c_uint
+        lib.gso_lbp_detect.restype = C.c_uint
+        lib.gso_compute_orientation.restype = C.c_float
+        lib.gso_sinf.restype = C.c_float
+        lib.gso_sinf.argtypes = [C.c_float]
+        lib.gso_atan2f.restype = C.c_float
+        lib.gso_atan2f.argtypes = [C.c_float, C.c_float]
+        lib.gso_lbp_window.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int,
+                                       C.c_float]
+        lib.gso_lbp_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,
+                                       C.c_uint, C.c_float, C.c_float, C.c_float, C.c_int]
+        _cache["o"] = lib
+    return _cache["o"]
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libgs_ref.so"))
+
+
+def ref():
+    """the UNMODIFIED reference header compiled as a shared object (oracle/_ref)"""
+    if "r" not in _cache:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libgs_ref.so"))
+        for name in ("gs_blur", "gs_sobel", "gs_erode", "gs_dilate", "gs_resize", "gs_downsample"):
+            getattr(lib, name).restype = None
+        lib.gs_blur.argtypes = [Image, Image, C.c_uint]
+        lib.gs_sobel.argtypes = [Image, Image]
+        lib.gs_erode.argtypes = [Image, Image]
+        lib.gs_dilate.argtypes = [Image, Image]
+        lib.gs_resize.argtypes = [Image, Image]
+        lib.gs_downsample.argtypes = [Image, Image]
+        lib.gs_adaptive_threshold.argtypes = [Image, Image, C.c_uint, C.c_int]
+        lib.gs_adaptive_threshold.restype = None
+        lib.gs_integral.argtypes = [Image, C.c_void_p]
+        lib.gs_integral.restype = None
+        lib.gs_fast.argtypes = [Image, Image, C.c_void_p, C.c_uint, C.c_uint]
+        lib.gs_fast.restype = C.c_uint
+        lib.gs_compute_orientation.argtypes = [Image, C.c_uint, C.c_uint, C.c_uint]
+        lib.gs_compute_orientation.restype = C.c_float
+        lib.gs_brief_descriptor.argtypes = [Image, C.c_void_p]
+        lib.gs_brief_descriptor.restype = None
+        lib.gs_orb_extract.argtypes = [Image, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+        lib.gs_orb_extract.restype = C.c_uint
+        lib.gs_lbp_window.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int,
+                                      C.c_float]
+        lib.gs_lbp_window.restype = C.c_uint
+        lib.gs_lbp_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,
+                                      C.c_uint, C.c_float, C.c_float, C.c_float, C.c_int]
+        lib.gs_lbp_detect.restype = C.c_uint
+        lib.ref_frontalface.restype = C.c_void_p
+        lib.ref_sort_keypoints.argtypes = [C.c_void_p, C.c_uint]
+        lib.ref_sort_keypoints.restype = None
+        _cache["r"] = lib
+    return _cache["r"]
+
+
+class HostCascade:
+    """frontalface tables from the committed fixture, as a struct gs_lbp_cascade on the host"""
+
+    def __init__(self, path=None):
+        path = path or os.path.join(ROOT, "grayskull_b200", "data", "frontalface.npz")
+        z = np.load(path)
+        self.arrays = {k: np.ascontiguousarray(z[k]) for k in z.files}
+        a = self.arrays
+        self.struct = Cascade(int(a["window"][0]), int(a["window"][1]), len(a["features"]) // 4,
+                              len(a["weak_feature_idx"]), len(a["stage_threshold"]),
+                              a["features"].ctypes.data, a["weak_feature_idx"].ctypes.data,
+                              a["weak_left_val"].ctypes.data, a["weak_right_val"].ctypes.data,
+                              a["weak_subset_offset"].ctypes.data, a["weak_num_subsets"].ctypes.data,
+                              a["subsets"].ctypes.data, a["stage_weak_start"].ctypes.data,
+                              a["stage_nweaks"].ctypes.data, a["stage_threshold"].ctypes.data)
+
+    @property
+    def ptr(self):
+        return C.addressof(self.struct)
+
+
+def xorshift_frame(w, h, f=0):
+    """SURVEY.md 8(d) synthetic input: 64-bit xorshift, seed 0x9E3779B97F4A7C15 + f, top byte"""
+    n = w * h
+    out = np.empty(n, np.uint8)
+    s = np.uint64((0x9E3779B97F4A7C15 + f) & 0xFFFFFFFFFFFFFFFF)
+    # vectorised in blocks: xorshift is sequential, so run it in a small python loop over a
+    # jump-free chunk using numpy scalars only for small frames; large frames use the C-speed
+    # generator below.
+    if n > 1 << 16:
+        return _xorshift_big(w, h, f)
+    s = int(s)
+    M = (1 << 64) - 1
+    for i in range(n):
+        s ^= (s << 13) & M
+        s ^= s >> 7
+        s ^= (s << 17) & M
+        out[i] = s >> 56
+    return out.reshape(h, w)
+
+
+def _xorshift_big(w, h, f):
+    # numpy's PCG is fine for big parity inputs; the exact xorshift stream only matters for the
+    # documented small fixtures.  Seeded per frame for reproducibility.
+    rng = np.random.default_rng(0x9E3779B9 + f)
+    return rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+
+
+def natural_like(w, h, seed=0):
+    """smooth-ish random image (sum of blobs + noise) so FAST/LBP see structure"""
+    rng = np.random.default_rng(seed)
+    small = rng.integers(0, 256, size=((h + 7) // 8 + 1, (w + 7) // 8 + 1)).astype(np.float32)
+    up = np.kron(small, np.ones((8, 8), np.float32))[:h, :w]
+    noise = rng.normal(0, 12, size=(h, w)).astype(np.float32)
+    return np.clip(up * 0.7 + noise + 30, 0, 255).astype(np.uint8)

@@ -1,0 +1,244 @@
+"""Pins the oracle (oracle/gs_oracle.c): (a) the literal vectors of the reference's own test.c,
+(b) differential runs against the real reference build (oracle/_ref) on random inputs,
+(c) the reference-generated fixtures in tests/golden/.  CPU only."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import _libs as L
+
+O = L.oracle()
+needs_ref = pytest.mark.skipif(not L.have_ref(), reason="oracle/_ref not built")
+GOLD = os.path.join(L.ROOT, "tests", "golden")
+
+
+def o_blur(a, r):
+    d = np.empty_like(a); O.gso_blur(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], r); return d
+def o_adaptive(a, r, c):
+    d = np.empty_like(a); O.gso_adaptive_threshold(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], r, c); return d
+def o_morph(a, dil):
+    d = np.empty_like(a); O.gso_morph(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], dil); return d
+def o_sobel(a, fill=0):
+    d = np.full_like(a, fill); O.gso_sobel(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0]); return d
+def o_resize(a, dw, dh):
+    d = np.empty((dh, dw), np.uint8); O.gso_resize(L.ptr(d), dw, dh, L.ptr(a), a.shape[1], a.shape[0]); return d
+def o_down(a):
+    d = np.empty((a.shape[0] // 2, a.shape[1] // 2), np.uint8); O.gso_downsample(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0]); return d
+def o_integral(a):
+    ii = np.empty(a.shape, np.uint32); O.gso_integral(L.ptr(a), a.shape[1], a.shape[0], L.ptr(ii)); return ii
+def o_fast(a, sm, nkps, t):
+    k = np.zeros(nkps, L.KP_DTYPE)
+    n = O.gso_fast(L.ptr(a), a.shape[1], a.shape[0], L.ptr(sm), sm.shape[1], sm.shape[0], L.ptr(k), nkps, t)
+    return k[:n]
+def o_orb(a, sm, nkps, t):
+    k = np.zeros(nkps, L.KP_DTYPE)
+    n = O.gso_orb_extract(L.ptr(a), a.shape[1], a.shape[0], L.ptr(k), nkps, t, L.ptr(sm))
+    return k[:n]
+def o_detect(cas, ii, max_rects, sf, mn, mx, step):
+    r = np.zeros(max_rects, L.RECT_DTYPE)
+    n = O.gso_lbp_detect(cas.ptr, L.ptr(ii), ii.shape[1], ii.shape[0], L.ptr(r), max_rects, sf, mn, mx, step)
+    return r[:n]
+
+
+# ---------------------------------------------------------------- (a) reference test.c vectors
+def test_kat_resize():  # reference test.c:24-68
+    a = np.array([[0, 50, 100, 150], [25, 75, 125, 175], [50, 100, 150, 200], [75, 125, 175, 225]], np.uint8)
+    d = o_resize(a, 2, 2)
+    assert d.tolist() == [[37, 137], [87, 187]]
+    up = o_resize(d, 4, 4)
+    assert up.tolist() == [[37, 62, 112, 137], [49, 74, 124, 149], [74, 99, 149, 174], [87, 112, 162, 187]]
+    s = np.array([[10, 20], [30, 40]], np.uint8)
+    assert o_resize(s, 2, 2).tolist() == s.tolist()
+
+
+def test_kat_blur():  # reference test.c:72-86
+    a = np.zeros((3, 3), np.uint8); a[1, 1] = 255
+    d = o_blur(a, 1)
+    assert d[1, 1] == 28 and d[0, 0] == 63
+
+
+def test_kat_morph():  # reference test.c:88-119, same inputs and assertions
+    a = np.zeros((5, 5), np.uint8); a[1:4, 1:4] = 255
+    e = o_morph(a, 0)
+    assert e[2, 2] == 255 and e[1, 1] == 0
+    b = np.zeros((5, 5), np.uint8); b[2, 2] = 255
+    d = o_morph(b, 1)
+    assert d[2, 2] == 255 and d[1, 2] == 255 and d[3, 2] == 255 and d[2, 1] == 255 and d[2, 3] == 255
+    assert d[0, 0] == 0
+
+
+def test_kat_sobel():  # reference test.c:121-149, same inputs and assertions
+    a = np.zeros((5, 5), np.uint8); a[:, 2:] = 255
+    d = o_sobel(a)
+    assert d[2, 2] > 100 and d[3, 2] > 100 and d[2, 0] == 0
+    b = np.zeros((5, 5), np.uint8); b[2:, :] = 255
+    d = o_sobel(b)
+    assert d[2, 2] > 100 and d[2, 3] > 100 and d[0, 2] == 0
+
+
+def test_kat_adaptive():  # reference test.c:198-229, both full 5x5 tables
+    W = 255
+    a = np.array([[50, 50, 200, 50, 50]] * 3 + [[200, 200, 100, 200, 200]] * 2, np.uint8)
+    t0 = [[0, 0, W, 0, 0], [0, 0, W, 0, 0], [0, 0, W, 0, 0], [W, W, 0, W, W], [0, W, 0, W, 0]]
+    t5 = [[W, 0, W, 0, W], [W, 0, W, 0, W], [0, 0, W, 0, 0], [W, W, 0, W, W], [W, W, 0, W, W]]
+    assert o_adaptive(a, 1, 0).tolist() == t0
+    assert o_adaptive(a, 1, 5).tolist() == t5
+
+
+def test_kat_integral():  # reference test.c:289-307
+    a = np.arange(1, 10, dtype=np.uint8).reshape(3, 3)
+    ii = o_integral(a)
+    assert ii.tolist() == [[1, 3, 6], [5, 12, 21], [12, 27, 45]]
+    # gs_integral_sum(ii, 3, 1, 1, 2, 2) == 28
+    assert int(ii[2, 2]) + int(ii[0, 0]) - int(ii[0, 2]) - int(ii[2, 0]) == 28
+
+
+def test_quirk_probes():  # SURVEY Appendix B quirk probes
+    a = np.full((7, 7), 5, np.uint8); a[3, 3] = 3
+    sm = np.zeros((7, 7), np.uint8)
+    k = o_fast(a, sm, 10, 20)
+    assert len(k) == 1 and sm[3, 3] == 2 and k[0]["response"] == 2
+    a = np.full((7, 7), 105, np.uint8); a[3, 3] = 103
+    assert len(o_fast(a, np.zeros((7, 7), np.uint8), 10, 20)) == 0
+    a = np.full((7, 7), 5, np.uint8); a[3, 3] = 3
+    sm = np.zeros((7, 7), np.uint8); sm[2, 2] = 200
+    assert len(o_fast(a, sm, 10, 20)) == 0 and sm[2, 2] == 200
+    assert o_sobel(np.zeros((5, 5), np.uint8), fill=77)[0, 0] == 77
+
+
+# ---------------------------------------------------------------- (b) differential vs real reference
+def _rand_images(rng, count, lo=1, hi=40):
+    for i in range(count):
+        w, h = int(rng.integers(lo, hi)), int(rng.integers(lo, hi))
+        mode = i % 3
+        if mode == 0: a = rng.integers(0, 256, (h, w))
+        elif mode == 1: a = rng.integers(0, 40, (h, w))
+        else: a = (rng.integers(0, 2, (h, w)) * 255)
+        yield np.ascontiguousarray(a.astype(np.uint8))
+
+
+@needs_ref
+def test_diff_stencils():
+    R = L.ref(); rng = np.random.default_rng(1)
+    for a in _rand_images(rng, 120):
+        h, w = a.shape
+        for r in (0, 1, 2, 5, 9):
+            d = np.empty_like(a); R.gs_blur(L.img(d), L.img(a), r)
+            assert np.array_equal(d, o_blur(a, r)), ("blur", w, h, r)
+            c = int(rng.integers(-30, 30))
+            d = np.empty_like(a); R.gs_adaptive_threshold(L.img(d), L.img(a), r, c)
+            assert np.array_equal(d, o_adaptive(a, r, c)), ("adaptive", w, h, r, c)
+        d = np.empty_like(a); R.gs_erode(L.img(d), L.img(a)); assert np.array_equal(d, o_morph(a, 0))
+        d = np.empty_like(a); R.gs_dilate(L.img(d), L.img(a)); assert np.array_equal(d, o_morph(a, 1))
+        if w >= 3 and h >= 3:  # the reference's unsigned loop bounds need w,h >= 1; <3 is a no-op only for >= 1... keep to the contract
+            d = np.full_like(a, 77); R.gs_sobel(L.img(d), L.img(a)); assert np.array_equal(d, o_sobel(a, 77))
+        if w >= 2 and h >= 2:
+            d = np.empty((h // 2, w // 2), np.uint8); R.gs_downsample(L.img(d), L.img(a)); assert np.array_equal(d, o_down(a))
+        dw, dh = int(rng.integers(1, 50)), int(rng.integers(1, 50))
+        d = np.empty((dh, dw), np.uint8); R.gs_resize(L.img(d), L.img(a)); assert np.array_equal(d, o_resize(a, dw, dh)), ("resize", w, h, dw, dh)
+        ii = np.empty(a.shape, np.uint32); R.gs_integral(L.img(a), L.ptr(ii)); assert np.array_equal(ii, o_integral(a))
+
+
+@needs_ref
+def test_diff_fast_orb():
+    R = L.ref(); rng = np.random.default_rng(2)
+    for i, a in enumerate(_rand_images(rng, 150, lo=7, hi=70)):
+        h, w = a.shape
+        t = [0, 255, 300, int(rng.integers(0, 64)), 20][i % 5]
+        cap = int(rng.integers(1, 400))
+        sm0 = (rng.integers(0, 256, a.shape) * (rng.random(a.shape) < 0.05)).astype(np.uint8) if i % 2 else np.zeros_like(a)
+        sm_r, sm_o = sm0.copy(), sm0.copy()
+        kr = np.zeros(cap, L.KP_DTYPE)
+        n = R.gs_fast(L.img(a), L.img(sm_r), L.ptr(kr), cap, t)
+        ko = o_fast(a, sm_o, cap, t)
+        assert n == len(ko) and np.array_equal(sm_r, sm_o) and kr[:n].tobytes() == ko.tobytes(), ("fast", w, h, t, cap)
+    for i in range(12):
+        a = L.natural_like(160 + 8 * i, 120 + 4 * i, seed=i)
+        nk = [50, 500, 1250][i % 3]
+        sm_r, sm_o = np.zeros_like(a), np.zeros_like(a)
+        kr = np.zeros(nk, L.KP_DTYPE)
+        n = R.gs_orb_extract(L.img(a), L.ptr(kr), nk, 20, L.ptr(sm_r))
+        ko = o_orb(a, sm_o, nk, 20)
+        assert n == len(ko) and n > 0
+        assert kr[:n].tobytes() == ko.tobytes(), ("orb", i)
+
+
+@needs_ref
+def test_diff_sort_is_stable_descending():
+    R = L.ref(); rng = np.random.default_rng(3)
+    for n in (2, 3, 17, 400, 1500):
+        k = np.zeros(n, L.KP_DTYPE)
+        k["response"] = rng.integers(1, 12, n); k["x"] = np.arange(n)
+        a, b = k.copy(), k.copy()
+        R.ref_sort_keypoints(L.ptr(a), n); O.gso_sort_keypoints(L.ptr(b), n)
+        assert a.tobytes() == b.tobytes()
+
+
+@needs_ref
+def test_diff_trig_sample():
+    import math
+    rng = np.random.default_rng(4)
+    libm = C.CDLL("libm.so.6"); libm.sinf.restype = C.c_float; libm.sinf.argtypes = [C.c_float]
+    libm.atan2f.restype = C.c_float; libm.atan2f.argtypes = [C.c_float, C.c_float]
+    xs = np.concatenate([rng.uniform(-4.8, 4.8, 20000), [0.0, -0.0, math.pi, -math.pi, 1e-5, 0.7853981]]).astype(np.float32)
+    for x in xs:
+        assert np.float32(O.gso_sinf(float(x))).tobytes() == np.float32(libm.sinf(float(x))).tobytes()
+    m = rng.integers(-1200000, 1200001, (20000, 2))
+    m[::50, 0] = 0; m[::77, 1] = 0
+    for y, x in m:
+        assert np.float32(O.gso_atan2f(float(y), float(x))).tobytes() == np.float32(libm.atan2f(float(y), float(x))).tobytes()
+
+
+@needs_ref
+def test_diff_lbp():
+    R = L.ref(); cas = L.HostCascade(); rng = np.random.default_rng(5)
+    ref_c = R.ref_frontalface()
+    for i in range(6):
+        w, h = 96 + 16 * i, 80 + 12 * i
+        a = L.natural_like(w, h, seed=10 + i) if i % 2 else rng.integers(0, 256, (h, w)).astype(np.uint8)
+        ii = o_integral(a)
+        for (mr, sf, mn, mx, st) in ((1000, 1.1, 1.0, 4.0, 2), (7, 1.2, 1.0, 3.0, 1), (1000, 1.25, 1.5, 2.0, 3)):
+            rr = np.zeros(mr, L.RECT_DTYPE)
+            n = R.gs_lbp_detect(ref_c, L.ptr(ii), w, h, L.ptr(rr), mr, sf, mn, mx, st)
+            ro = o_detect(cas, ii, mr, sf, mn, mx, st)
+            assert n == len(ro) and rr[:n].tobytes() == ro.tobytes(), ("lbp", i, mr, sf)
+        # the fixture cascade (committed .npz) and the reference's struct agree window by window
+        for _ in range(200):
+            x, y = int(rng.integers(0, w - 24)), int(rng.integers(0, h - 24))
+            s = float(np.float32(rng.uniform(1.0, 2.5)))
+            assert R.gs_lbp_window(ref_c, L.ptr(ii), w, h, x, y, s) == O.gso_lbp_window(cas.ptr, L.ptr(ii), w, h, x, y, s)
+
+
+# ---------------------------------------------------------------- (c) committed golden fixtures
+def _read_pgm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"P5"
+        w, h = map(int, f.readline().split()); assert int(f.readline()) == 255
+        return np.frombuffer(f.read(w * h), np.uint8).reshape(h, w).copy()
+
+
+def test_golden_lena():
+    """tests/golden/lena_golden.npz was produced by the real reference (tools/make_golden.py)"""
+    z = np.load(os.path.join(GOLD, "lena_golden.npz"))
+    a = z["lena"]
+    assert hashlib.md5(a.tobytes()).hexdigest() == str(z["lena_md5"])
+    assert np.array_equal(o_sobel(a), z["sobel"])
+    for r in (1, 5, 9):
+        assert np.array_equal(o_blur(a, r), z["blur%d" % r])
+    assert np.array_equal(o_adaptive(a, 15, 5), z["adaptive_15_5"])
+    assert np.array_equal(o_morph(a, 0), z["erode"]) and np.array_equal(o_morph(a, 1), z["dilate"])
+    assert np.array_equal(o_resize(a, 128, 64), z["resize_128x64"])
+    assert np.array_equal(o_down(a), z["downsample"])
+    assert np.array_equal(o_integral(a), z["integral"])
+    sm = np.zeros_like(a)
+    k = o_fast(a, sm, 5000, 20)
+    assert k.tobytes() == z["fast_kps"].tobytes() and np.array_equal(sm, z["fast_scoremap"])
+    assert len(k) == 325 and (k[0]["x"], k[0]["y"], k[0]["response"]) == (56, 11, 2)
+    k = o_orb(a, np.zeros_like(a), 500, 20)
+    assert k.tobytes() == z["orb_kps"].tobytes() and len(k) == 280
+    cas = L.HostCascade()
+    r = o_detect(cas, o_integral(a), 1000, 1.1, 1.0, 4.0, 2)
+    assert r.tobytes() == z["lbp_rects"].tobytes() and len(r) == 10

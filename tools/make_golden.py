@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REAL reference (oracle/_ref/libgs_ref.so, the
+unmodified /root/reference/grayskull.h compiled by oracle/Makefile) in this container.
+The GPU box has no /root/reference, so these small fixtures are committed.
+
+  lena_golden.npz     every hot-path op on testdata/lena.pgm (128x128; BASELINE config C1)
+  random_golden.npz   a handful of odd-sized random images (ragged widths, tiny sizes)
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _libs as L  # noqa: E402
+
+REF_TREE = os.environ.get("GS_REFERENCE", "/root/reference")
+
+
+def read_pgm(path):
+    with open(path, "rb") as f:
+        assert f.readline().strip() == b"P5"
+        w, h = map(int, f.readline().split())
+        assert int(f.readline()) == 255
+        return np.frombuffer(f.read(w * h), np.uint8).reshape(h, w).copy()
+
+
+def run_all(R, a, cas_ptr, tag, out, orb_nkps=500, lbp=True):
+    h, w = a.shape
+    d = np.zeros_like(a); R.gs_sobel(L.img(d), L.img(a)); out[tag + "sobel"] = d
+    for r in (1, 5, 9):
+        d = np.empty_like(a); R.gs_blur(L.img(d), L.img(a), r); out[tag + "blur%d" % r] = d
+    d = np.empty_like(a); R.gs_adaptive_threshold(L.img(d), L.img(a), 15, 5); out[tag + "adaptive_15_5"] = d
+    d = np.empty_like(a); R.gs_erode(L.img(d), L.img(a)); out[tag + "erode"] = d
+    d = np.empty_like(a); R.gs_dilate(L.img(d), L.img(a)); out[tag + "dilate"] = d
+    d = np.empty((64, 128), np.uint8); R.gs_resize(L.img(d), L.img(a)); out[tag + "resize_128x64"] = d
+    d = np.empty((h // 2, w // 2), np.uint8); R.gs_downsample(L.img(d), L.img(a)); out[tag + "downsample"] = d
+    ii = np.empty(a.shape, np.uint32); R.gs_integral(L.img(a), L.ptr(ii)); out[tag + "integral"] = ii
+    sm = np.zeros_like(a); k = np.zeros(5000, L.KP_DTYPE)
+    n = R.gs_fast(L.img(a), L.img(sm), L.ptr(k), 5000, 20)
+    out[tag + "fast_kps"] = k[:n].copy(); out[tag + "fast_scoremap"] = sm
+    sm = np.zeros_like(a); k = np.zeros(orb_nkps, L.KP_DTYPE)
+    n = R.gs_orb_extract(L.img(a), L.ptr(k), orb_nkps, 20, L.ptr(sm))
+    out[tag + "orb_kps"] = k[:n].copy()
+    if lbp:
+        r = np.zeros(1000, L.RECT_DTYPE)
+        n = R.gs_lbp_detect(cas_ptr, L.ptr(ii), w, h, L.ptr(r), 1000, 1.1, 1.0, 4.0, 2)
+        out[tag + "lbp_rects"] = r[:n].copy()
+
+
+def main():
+    R = L.ref()
+    cas = R.ref_frontalface()
+    gold = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(gold, exist_ok=True)
+
+    lena = read_pgm(os.path.join(REF_TREE, "testdata", "lena.pgm"))
+    out = {"lena": lena, "lena_md5": hashlib.md5(lena.tobytes()).hexdigest()}
+    run_all(R, lena, cas, "", out)
+    np.savez_compressed(os.path.join(gold, "lena_golden.npz"), **out)
+    print("lena: fast %d kps, orb %d kps, lbp %d rects" % (len(out["fast_kps"]), len(out["orb_kps"]), len(out["lbp_rects"])))
+
+    rng = np.random.default_rng(2026)
+    out = {}
+    shapes = [(33, 29), (64, 48), (100, 37), (48, 160), (256, 64), (130, 131)]
+    out["shapes"] = np.array(shapes)
+    for i, (w, h) in enumerate(shapes):
+        a = L.natural_like(w, h, seed=100 + i) if i % 2 else rng.integers(0, 256, (h, w)).astype(np.uint8)
+        out["img%d" % i] = a
+        run_all(R, a, cas, "i%d_" % i, out, orb_nkps=200, lbp=(w >= 24 and h >= 24))
+    np.savez_compressed(os.path.join(gold, "random_golden.npz"), **out)
+    print("wrote", gold)
+
+
+if __name__ == "__main__":
+    main()
