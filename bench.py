@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the grayskull hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|ops] [--impl reference]
+
+Default workload = BASELINE.json configs[1] ("c2"): gs_blur r=5 + gs_sobel on 4096x4096 synthetic
+uint8 frames, batch 256 per GPU (weak scaling: every rank processes its own 256 frames; frames are
+independent, no data-path collective).  A step = one pass of both ops over the batch.
+
+One JSON line on stdout (rank 0):
+  value      Mpixels/s, whole job, inputs resident in HBM, CUDA-event time, max over ranks
+  e2e        the same metric through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H in
+             the timed region, chunked over two streams
+  roofline   dominant kernel's algorithmic HBM bytes / its own CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own C code (oracle/_ref, built from /root/reference) timed on this
+             box's host cores on a bounded sample of the same workload
+With --impl reference the whole line is the reference CPU arm (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+W2, H2, B2, R2 = 4096, 4096, 256, 5            # c2
+W3, H3, B3, NK3, T3 = 1920, 1080, 1024, 1250, 20   # c3
+W4, H4, B4 = 3840, 2160, 256                  # c4 (sf 1.1, scales 1..4, step 2, max_rects 65536)
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+# ------------------------------------------------------------------ reference CPU arm
+def _cpu_worker(args):
+    """one process: run the real reference (or the oracle port) on `nframes` frames"""
+    kind, workload, seed, nframes = args
+    import numpy as np
+    import _libs as L
+    units = 0
+    busy = 0.0
+    if kind == "reference":
+        R = L.ref()
+    else:
+        O = L.oracle()
+    for i in range(nframes):
+        rng = np.random.default_rng(seed * 1000 + i)
+        if workload == "c2":
+            a = rng.integers(0, 256, (H2, W2), dtype=np.uint8)
+            b = np.empty_like(a); s = np.zeros_like(a)
+            t0 = time.perf_counter()
+            if kind == "reference":
+                R.gs_blur(L.img(b), L.img(a), R2); R.gs_sobel(L.img(s), L.img(b))
+            else:
+                O.gso_blur(L.ptr(b), L.ptr(a), W2, H2, R2); O.gso_sobel(L.ptr(s), L.ptr(b), W2, H2)
+            units += W2 * H2
+        elif workload == "c3":
+            a = L.natural_like(W3, H3, seed * 1000 + i)
+            k = np.zeros(NK3, L.KP_DTYPE); sm = np.zeros_like(a)
+            t0 = time.perf_counter()
+            if kind == "reference":
+                R.gs_orb_extract(L.img(a), L.ptr(k), NK3, T3, L.ptr(sm))
+            else:
+                O.gso_orb_extract(L.ptr(a), W3, H3, L.ptr(k), NK3, T3, L.ptr(sm))
+            units += W3 * H3
+        else:  # c4
+            a = L.natural_like(W4, H4, seed * 1000 + i)
+            ii = np.empty(a.shape, np.uint32); r = np.zeros(65536, L.RECT_DTYPE)
+            cas = None if kind == "reference" else L.HostCascade()
+            t0 = time.perf_counter()
+            if kind == "reference":
+                R.gs_integral(L.img(a), L.ptr(ii))
+                R.gs_lbp_detect(R.ref_frontalface(), L.ptr(ii), W4, H4, L.ptr(r), 65536, 1.1, 1.0, 4.0, 2)
+            else:
+                O.gso_integral(L.ptr(a), W4, H4, L.ptr(ii))
+                O.gso_lbp_detect(cas.ptr, L.ptr(ii), W4, H4, L.ptr(r), 65536, 1.1, 1.0, 4.0, 2)
+            units += 30016520
+        busy += time.perf_counter() - t0
+    return units, busy
+
+
+def cpu_reference(workload, steps=1, warmup=0, frames_per_core=1, max_cores=None):
+    """Frame-parallel over the host cores (one process per core: gs_orb_extract's static buffer is
+    not thread-safe, reference grayskull.h:655).  Returns (value per second, dict)."""
+    import _libs as L
+    kind = "reference" if L.have_ref() else "port"
+    if kind == "port":
+        L.oracle()
+    cores = len(os.sched_getaffinity(0))
+    if max_cores:
+        cores = min(cores, max_cores)
+    ctx = mp.get_context("fork")
+    per_step = []
+    with ctx.Pool(cores) as pool:
+        for s in range(warmup + steps):
+            res = pool.map(_cpu_worker, [(kind, workload, s * 64 + c, frames_per_core) for c in range(cores)])
+            if s >= warmup:   # all cores run concurrently: the step takes as long as the slowest one
+                per_step.append((sum(u for u, _ in res), max(t for _, t in res)))
+    units = sum(u for u, _ in per_step)
+    secs = sum(t for _, t in per_step)
+    unit_name = "Mpixels/s" if workload in ("c2", "c3") else "windows/s"
+    scale = 1e-6 if workload in ("c2", "c3") else 1.0
+    sample = {"c2": "%d frames of 4096x4096 per step, gs_blur r=5 + gs_sobel" % (cores * frames_per_core),
+              "c3": "%d frames of 1920x1080 per step, gs_orb_extract nkps=1250 t=20" % (cores * frames_per_core),
+              "c4": "%d frames of 3840x2160 per step, gs_integral + gs_lbp_detect" % (cores * frames_per_core)}[workload]
+    return units / secs * scale, {"value": units / secs * scale, "unit": unit_name, "cores": cores, "kind": kind,
+                                 "sample": sample + " (gcc -std=c99 -O2, one process per core)",
+                                 "ms_per_step": 1e3 * secs / max(len(per_step), 1)}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], 0, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, cmax, power, util = float(parts[0]), float(parts[1]), float(parts[2]), float(parts[3])
+            except ValueError:
+                continue
+            mx = max(mx, cmax)
+            if util >= 50:
+                sm.append(clk); pw.append(power)
+                for nme, v in zip(names, parts[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "power_w": statistics.median(pw) if pw else None, "samples_under_load": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ GPU arm
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+    import grayskull_b200 as g
+    from grayskull_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib = g.lib()
+    g._lib.check(lib.gs_b200_set_device(local), "set_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def time_steps(fn, steps, warmup):
+        """W warm-ups, then K steps between barrier+sync, CUDA events on the launching stream"""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    hbm, peak_kind = peaks()
+    wl = args.workload
+    torch.manual_seed(1234 + rank)
+    extra = {}
+
+    if wl == "c2":
+        n, h, w = args.batch or B2, H2, W2
+        src = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=dev)
+        blur = torch.empty_like(src)
+        sob = torch.zeros_like(src)
+
+        def step():
+            api.blur_batch(src, R2, out=blur)
+            api.sobel_batch(blur, out=sob)
+
+        units_per_step = n * h * w
+        unit, scale, metric = "Mpixels/s", 1e-6, "Mpixels/s, gs_blur(r=5) + gs_sobel, 4096x4096 uint8"
+        cfg = {"workload": "c2: gs_blur r=5 + gs_sobel, 4096x4096 synthetic uint8, batch %d per GPU" % n,
+               "frames_per_gpu": n, "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (n * h * w / 2**30)}
+        kernels = {"gs_blur_r5": (lambda: api.blur_batch(src, R2, out=blur), 2.0 * n * h * w),
+                   "gs_sobel": (lambda: api.sobel_batch(blur, out=sob), 1.0 * n * h * w + 1.0 * n * (h - 2) * (w - 2))}
+        launches_per_step = 2
+    elif wl == "c3":
+        n, h, w = args.batch or B3, H3, W3
+        noise = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=dev)
+        src = api.blur_batch(noise, 3)      # "blurred noise": natural-image-like autocorrelation
+        del noise
+        sm = torch.zeros_like(src)
+
+        def step():
+            api.orb_extract_batch(src, NK3, T3, scoremap=sm)
+
+        units_per_step = n * h * w
+        unit, scale, metric = "Mpixels/s", 1e-6, "Mpixels/s, gs_orb_extract (FAST-9 t=20 + BRIEF-256, nkps=1250), 1920x1080 uint8"
+        cfg = {"workload": "c3: gs_orb_extract nkps=1250 t=20, 1920x1080 blurred-noise uint8, batch %d per GPU" % n,
+               "frames_per_gpu": n, "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (n * h * w / 2**30)}
+        kernels = {"gs_orb_extract": (step, 2.0 * n * h * w)}
+        launches_per_step = 6
+    elif wl == "c4":
+        n, h, w = args.batch or B4, H4, W4
+        cas = g.load_cascade()
+        noise = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=dev)
+        src = api.blur_batch(noise, 3)
+        del noise
+        ii = torch.empty((n, h, w), dtype=torch.int32, device=dev)
+        nwin = api.lbp_window_count(cas, w, h, 1.1, 1.0, 4.0, 2)
+
+        def step():
+            api.integral_batch(src, out=ii)
+            api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2)
+
+        units_per_step = n * nwin
+        unit, scale, metric = "windows/s", 1.0, "LBP cascade windows/s, gs_integral + gs_lbp_detect frontalface, 3840x2160"
+        cfg = {"workload": "c4: gs_integral + gs_lbp_detect frontalface sf=1.1 scales 1..4 step=2, 3840x2160, batch %d per GPU" % n,
+               "frames_per_gpu": n, "windows_per_frame": nwin,
+               "l2": "integral tables (%.1f GiB per GPU) exceed the 126 MB L2" % (n * h * w * 4 / 2**30)}
+        kernels = {"gs_integral": (lambda: api.integral_batch(src, out=ii), 5.0 * n * h * w),
+                   "gs_lbp_detect": (lambda: api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2), 4.0 * n * h * w)}
+        launches_per_step = 5
+    else:
+        raise SystemExit("unknown workload " + wl)
+
+    # ---- headline: device-resident steps ----
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.gs_b200_launch_count()
+    ms = time_steps(step, args.steps, args.warmup)
+    launches = (lib.gs_b200_launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if sampler else None
+    value = units_per_step * world * args.steps / (ms * 1e-3) * scale
+
+    # ---- per-kernel CUDA-event timing (roofline) ----
+    kres = {}
+    for name, (fn, algo_bytes) in kernels.items():
+        kms = time_steps(fn, max(args.steps // 2, 5), 3) / max(args.steps // 2, 5)
+        kres[name] = {"ms": kms, "algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (kms * 1e-3) / 1e9,
+                      "frac": algo_bytes / (kms * 1e-3) / 1e9 / hbm}
+    dom = max(kres, key=lambda k: kres[k]["ms"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(wl, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kres[dom]["achieved_gbs"], "peak": hbm,
+                "peak_source": peak_kind + (" (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else " (B200_PROFILING.md)"),
+                "unit": "GB/s", "frac": kres[dom]["frac"], "traffic": traffic,
+                "algorithmic_bytes_per_launch": kres[dom]["algorithmic_bytes"], "ms_per_launch": kres[dom]["ms"]}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if wl == "c2" and not args.no_e2e:
+        ne = min(n, args.e2e_frames)
+        chunk = 16
+        hin = torch.empty((ne, h, w), dtype=torch.uint8).pin_memory()
+        hout = torch.empty((ne, h, w), dtype=torch.uint8).pin_memory()
+        hin.copy_(src[:ne].cpu())
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        dbuf = [(torch.empty((chunk, h, w), dtype=torch.uint8, device=dev), torch.empty((chunk, h, w), dtype=torch.uint8, device=dev),
+                 torch.zeros((chunk, h, w), dtype=torch.uint8, device=dev)) for _ in range(2)]
+        fb = chunk * h * w
+
+        def e2e_step():
+            for ci, lo in enumerate(range(0, ne, chunk)):
+                st = streams[ci & 1]
+                a, b, c = dbuf[ci & 1]
+                sp = C.c_void_p(st.cuda_stream)
+                k = min(chunk, ne - lo)
+                g._lib.check(lib.gs_b200_memcpy_h2d(C.c_void_p(a.data_ptr()), C.c_void_p(hin[lo].data_ptr()), k * h * w, sp))
+                g._lib.check(lib.gs_b200_blur_batch(C.c_void_p(b.data_ptr()), C.c_void_p(a.data_ptr()), w, h, k, R2, sp))
+                g._lib.check(lib.gs_b200_sobel_batch(C.c_void_p(c.data_ptr()), C.c_void_p(b.data_ptr()), w, h, k, sp))
+                g._lib.check(lib.gs_b200_memcpy_d2h(C.c_void_p(hout[lo].data_ptr()), C.c_void_p(c.data_ptr()), k * h * w, sp))
+            for st in streams:
+                st.synchronize()
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        ksteps = max(3, args.steps // 10)
+        for _ in range(ksteps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": ne * h * w * world * ksteps / dt * scale, "unit": unit, "h2d_bytes_per_step": ne * h * w,
+               "d2h_bytes_per_step": ne * h * w, "frames_per_step": ne, "steps": ksteps,
+               "path": "pinned host -> gs_b200_memcpy_h2d -> gs_b200_blur_batch -> gs_b200_sobel_batch -> gs_b200_memcpy_d2h, 16-frame chunks on 2 streams"}
+        del hin, hout, dbuf
+
+    # ---- CPU baseline (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        _, cpu = cpu_reference(wl, steps=1, warmup=0)
+
+    if rank == 0:
+        out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8" if wl != "c4" else "u32", "data": "synthetic", "config": cfg, "clocks": clocks,
+               "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
+               "roofline": roofline, "kernels": kres, "cpu_baseline": cpu,
+               "tma_path": bool(lib.gs_b200_uses_tma(w, h, src.data_ptr()))}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_main(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    value, cpu = cpu_reference(wl, steps=max(1, min(args.steps, 5)), warmup=min(args.warmup, 1))
+    unit = cpu["unit"]
+    metric = {"c2": "Mpixels/s, gs_blur(r=5) + gs_sobel, 4096x4096 uint8",
+              "c3": "Mpixels/s, gs_orb_extract (FAST-9 t=20 + BRIEF-256, nkps=1250), 1920x1080 uint8",
+              "c4": "LBP cascade windows/s, gs_integral + gs_lbp_detect frontalface, 3840x2160"}[wl]
+    out = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": cpu["ms_per_step"],
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if wl != "c4" else "u32",
+           "data": "synthetic", "config": {"workload": cpu["sample"]}, "cpu_baseline": cpu,
+           "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
+    ap.add_argument("--e2e-frames", type=int, default=64)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference_main(a)
+    else:
+        gpu_main(a)

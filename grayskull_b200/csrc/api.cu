@@ -1,0 +1,240 @@
+// api.cu -- the reference's single-image gs_* entry points (include/grayskull.h) on top of the
+// batched kernels: n == 1, legacy default stream, synchronous.  Device / managed pointers are
+// used in place; plain host pointers are staged through the library's device workspace (copied
+// in, processed, copied back), so unmodified callers such as the reference's test.c work.
+// Precondition checks are the reference's gs_assert conditions (cited), CUDA failures abort with
+// a message: there is no CPU fallback anywhere in this library.
+#include <string.h>
+
+#include "common.cuh"
+
+extern "C" {
+int gsb_fast_single(const uint8_t *src, unsigned w, unsigned h, uint8_t *score, unsigned sw, unsigned sh,
+                    struct gs_keypoint *kps, unsigned *count, unsigned nkps, unsigned threshold, cudaStream_t s);
+int gsb_orient_single(const uint8_t *img, unsigned w, unsigned x, unsigned y, unsigned r, float *out, cudaStream_t s);
+int gsb_brief_single(const uint8_t *img, unsigned w, unsigned h, struct gs_keypoint *kp, cudaStream_t s);
+int gsb_lbp_window_single(const struct gs_lbp_cascade *c, const uint32_t *ii, unsigned iw, unsigned ih, int x, int y,
+                          float scale, unsigned *out_dev, cudaStream_t s);
+}
+
+namespace {
+
+void die(const char *what, int rc) {
+  fprintf(stderr, "grayskull_b200: %s failed: %s\n", what, rc ? gs_b200_last_error() : "(no device?)");
+  abort();
+}
+#define GS_DO(call)                \
+  do {                             \
+    int rc_ = (call);              \
+    if (rc_) die(#call, rc_);      \
+  } while (0)
+#define GS_CUDA(call)                                           \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if (e_ != cudaSuccess) die(#call, gsb::record_error(e_, __FILE__, __LINE__)); \
+  } while (0)
+
+bool on_device(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+inline int gs_ok(struct gs_image img) { return img.data && img.w > 0 && img.h > 0; }
+
+// a buffer that lives on the device for the duration of one call
+struct Buf {
+  void *dev = nullptr;
+  void *host = nullptr;  // non-null iff staged
+  size_t bytes = 0;
+};
+Buf in_buf(const void *p, size_t bytes, int slot, bool copy_in = true) {
+  Buf b;
+  b.bytes = bytes;
+  if (!p || bytes == 0) return b;
+  if (on_device(p)) {
+    b.dev = const_cast<void *>(p);
+    return b;
+  }
+  b.dev = gsb::workspace(0, slot, bytes);
+  if (!b.dev) die("device workspace allocation", 1);
+  b.host = const_cast<void *>(p);
+  if (copy_in) GS_CUDA(cudaMemcpyAsync(b.dev, p, bytes, cudaMemcpyHostToDevice, 0));
+  return b;
+}
+void out_buf(const Buf &b, size_t bytes = ~(size_t)0) {
+  if (b.host) GS_CUDA(cudaMemcpyAsync(b.host, b.dev, bytes < b.bytes ? bytes : b.bytes, cudaMemcpyDeviceToHost, 0));
+}
+void finish() { GS_CUDA(cudaStreamSynchronize(0)); }
+
+}  // namespace
+
+extern "C" {
+
+void gs_blur(struct gs_image dst, struct gs_image src, unsigned radius) {
+  GSB_ASSERT(gs_ok(src) && gs_ok(dst) && dst.w == src.w && dst.h == src.h);  // reference :269
+  const size_t n = (size_t)src.w * src.h;
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_blur_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, radius, 0));
+  out_buf(d);
+  finish();
+}
+
+void gs_adaptive_threshold(struct gs_image dst, struct gs_image src, unsigned radius, int c) {
+  GSB_ASSERT(gs_ok(dst) && gs_ok(src) && dst.w == src.w && dst.h == src.h);  // reference :232
+  const size_t n = (size_t)src.w * src.h;
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_adaptive_threshold_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, radius, c, 0));
+  out_buf(d);
+  finish();
+}
+
+void gs_sobel(struct gs_image dst, struct gs_image src) {
+  GSB_ASSERT(gs_ok(dst) && gs_ok(src) && dst.w == src.w && dst.h == src.h);  // reference :307
+  const size_t n = (size_t)src.w * src.h;
+  // dst is copied in as well: its 1-px frame must keep the caller's bytes (reference :308-309)
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, true);
+  GS_DO(gs_b200_sobel_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  out_buf(d);
+  finish();
+}
+
+static void morph(struct gs_image dst, struct gs_image src, int dilate) {
+  GSB_ASSERT(gs_ok(dst) && gs_ok(src) && dst.w == src.w && dst.h == src.h);  // reference :287
+  const size_t n = (size_t)src.w * src.h;
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
+  if (dilate) GS_DO(gs_b200_dilate_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  else GS_DO(gs_b200_erode_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  out_buf(d);
+  finish();
+}
+void gs_erode(struct gs_image dst, struct gs_image src) { morph(dst, src, 0); }
+void gs_dilate(struct gs_image dst, struct gs_image src) { morph(dst, src, 1); }
+
+void gs_resize(struct gs_image dst, struct gs_image src) {
+  GSB_ASSERT(gs_ok(dst) && gs_ok(src));  // reference :172
+  Buf s = in_buf(src.data, (size_t)src.w * src.h, gsb::WS_STAGE_A);
+  Buf d = in_buf(dst.data, (size_t)dst.w * dst.h, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_resize_batch((uint8_t *)d.dev, dst.w, dst.h, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  out_buf(d);
+  finish();
+}
+
+void gs_downsample(struct gs_image dst, struct gs_image src) {
+  GSB_ASSERT(gs_ok(src) && gs_ok(dst) && dst.w == src.w / 2 && dst.h == src.h / 2);  // reference :190
+  Buf s = in_buf(src.data, (size_t)src.w * src.h, gsb::WS_STAGE_A);
+  Buf d = in_buf(dst.data, (size_t)dst.w * dst.h, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_downsample_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  out_buf(d);
+  finish();
+}
+
+void gs_integral(struct gs_image src, unsigned *ii) {
+  GSB_ASSERT(gs_ok(src) && ii);  // reference :745
+  const size_t n = (size_t)src.w * src.h;
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(ii, n * 4, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_integral_batch((uint32_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  out_buf(d);
+  finish();
+}
+
+unsigned gs_fast(struct gs_image img, struct gs_image scoremap, struct gs_keypoint *kps, unsigned nkps,
+                 unsigned threshold) {
+  GSB_ASSERT(gs_ok(img) && kps && nkps > 0);  // reference :484
+  Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  // an invalid score map drops every write and reads as 0 (gs_get/gs_set, reference :143-148)
+  unsigned sw = gs_ok(scoremap) ? scoremap.w : 0, sh = gs_ok(scoremap) ? scoremap.h : 0;
+  Buf m = in_buf(sw ? scoremap.data : nullptr, (size_t)sw * sh, gsb::WS_STAGE_B, true);
+  Buf k = in_buf(kps, sizeof(struct gs_keypoint) * (size_t)nkps, gsb::WS_STAGE_C, false);
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!cnt) die("device workspace allocation", 1);
+  uint8_t *mp = sw ? (uint8_t *)m.dev : (uint8_t *)cnt;  // never dereferenced when sw == 0
+  GS_DO(gsb_fast_single((const uint8_t *)s.dev, img.w, img.h, mp, sw, sh, (struct gs_keypoint *)k.dev, cnt, nkps,
+                        threshold, 0));
+  unsigned n = 0;
+  GS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof(n), cudaMemcpyDeviceToHost, 0));
+  finish();
+  out_buf(m);
+  out_buf(k, sizeof(struct gs_keypoint) * (size_t)n);
+  finish();
+  return n;
+}
+
+float gs_compute_orientation(struct gs_image img, unsigned x, unsigned y, unsigned r) {
+  GSB_ASSERT(gs_ok(img) && x >= r && y >= r && x < img.w - r && y < img.h - r);  // reference :609
+  Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  float *out = static_cast<float *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!out) die("device workspace allocation", 1);
+  GS_DO(gsb_orient_single((const uint8_t *)s.dev, img.w, x, y, r, out, 0));
+  float a = 0;
+  GS_CUDA(cudaMemcpyAsync(&a, out, sizeof(a), cudaMemcpyDeviceToHost, 0));
+  finish();
+  return a;
+}
+
+void gs_brief_descriptor(struct gs_image img, struct gs_keypoint *kp) {
+  GSB_ASSERT(gs_ok(img) && kp);  // reference :624
+  Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  Buf k = in_buf(kp, sizeof(struct gs_keypoint), gsb::WS_STAGE_C, true);
+  GS_DO(gsb_brief_single((const uint8_t *)s.dev, img.w, img.h, (struct gs_keypoint *)k.dev, 0));
+  out_buf(k);
+  finish();
+}
+
+unsigned gs_orb_extract(struct gs_image img, struct gs_keypoint *kps, unsigned nkps, unsigned threshold,
+                        uint8_t *scoremap_buffer) {
+  GSB_ASSERT(gs_ok(img) && kps && nkps > 0 && scoremap_buffer);  // reference :653
+  const size_t n = (size_t)img.w * img.h;
+  Buf s = in_buf(img.data, n, gsb::WS_STAGE_A), m = in_buf(scoremap_buffer, n, gsb::WS_STAGE_B, true);
+  Buf k = in_buf(kps, sizeof(struct gs_keypoint) * (size_t)nkps, gsb::WS_STAGE_C, false);
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!cnt) die("device workspace allocation", 1);
+  GS_DO(gs_b200_orb_extract_batch((const uint8_t *)s.dev, img.w, img.h, 1, (uint8_t *)m.dev,
+                                  (struct gs_keypoint *)k.dev, cnt, nkps, threshold, 0));
+  unsigned c = 0;
+  GS_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, 0));
+  finish();
+  out_buf(m);
+  out_buf(k, sizeof(struct gs_keypoint) * (size_t)c);
+  finish();
+  return c;
+}
+
+unsigned gs_lbp_window(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw, unsigned ih, int x, int y,
+                       float scale) {
+  GSB_ASSERT(c && ii);
+  const int win_w = (int)((float)c->window_w * scale), win_h = (int)((float)c->window_h * scale);
+  if (x + win_w > (int)iw || y + win_h > (int)ih) return 0;  // reference :793
+  Buf t = in_buf(ii, (size_t)iw * ih * 4, gsb::WS_STAGE_A);
+  unsigned *out = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!out) die("device workspace allocation", 1);
+  GS_DO(gsb_lbp_window_single(c, (const uint32_t *)t.dev, iw, ih, x, y, scale, out, 0));
+  unsigned r = 0;
+  GS_CUDA(cudaMemcpyAsync(&r, out, sizeof(r), cudaMemcpyDeviceToHost, 0));
+  finish();
+  return r;
+}
+
+unsigned gs_lbp_detect(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw, unsigned ih,
+                       struct gs_rect *rects, unsigned max_rects, float scale_factor, float min_scale,
+                       float max_scale, int step) {
+  GSB_ASSERT(c && ii);
+  if (max_rects == 0) return 0;
+  Buf t = in_buf(ii, (size_t)iw * ih * 4, gsb::WS_STAGE_A);
+  Buf r = in_buf(rects, sizeof(struct gs_rect) * (size_t)max_rects, gsb::WS_STAGE_C, false);
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!cnt) die("device workspace allocation", 1);
+  GS_DO(gs_b200_lbp_detect_batch(c, (const uint32_t *)t.dev, iw, ih, 1, (struct gs_rect *)r.dev, cnt, max_rects,
+                                 scale_factor, min_scale, max_scale, step, 0));
+  unsigned n = 0;
+  GS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof(n), cudaMemcpyDeviceToHost, 0));
+  finish();
+  out_buf(r, sizeof(struct gs_rect) * (size_t)n);
+  finish();
+  return n;
+}
+
+}  // extern "C"

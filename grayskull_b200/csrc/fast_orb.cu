@@ -1,0 +1,500 @@
+// fast_orb.cu -- gs_fast, gs_compute_orientation, gs_brief_descriptor, gs_orb_extract
+// (reference grayskull.h:482-669).
+//
+// gs_fast      pass 1  k_fast_score : FAST-9 score map, interior pixels only.  16-bit brighter /
+//                                     darker ring masks; "run of >= 9" is the rotate-AND test; the
+//                                     unsigned-wrap quirk of reference :498 (p < t => every
+//                                     non-brighter sample counts as darker) is reproduced.
+//              pass 2  k_nms_count -> k_row_scan -> k_nms_emit : 3x3 strict-greater NMS over the
+//                                     caller's score map (including the ring cells pass 1 never
+//                                     writes, exactly like reference :517-524) and a SCAN-based
+//                                     compaction, because the reference emits keypoints in raster
+//                                     order and stops at nkps (:530).
+// gs_orb_extract       k_orb_select : one CTA per frame: stable descending counting sort on the
+//                                     8-bit response (== the reference's bubble sort, :639-649),
+//                                     15-px margin filter and cap, all order-preserving.
+//                      k_orb_describe: one warp per keypoint: the r=15 disc moments in int32
+//                                     (exact, lanes = dx), atan2f, sinf, and BRIEF-256 where each
+//                                     ballot yields one descriptor word.
+// The reference calls libm atan2f / sinf (grayskull.h:100-101); trig mode 0 evaluates glibc
+// 2.39's algorithms with IEEE-exact device arithmetic (see dev_sinf / dev_atan2f), so angles and
+// descriptors are bit-identical to the reference on the same box.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace gsb {
+
+static int g_trig_mode = 0;
+
+__constant__ uint32_t c_brief[256] = {
+#include "brief_pattern.inc"
+};
+
+// ---------------------------------------------------------------------------------------------
+// glibc 2.39 sinf (sysdeps/ieee754/flt-32/s_sinf.c, sincosf.h; double evaluation) and atan2f /
+// atanf (e_atan2f.c, s_atanf.c; float evaluation), restated with explicitly rounded ops.
+// tools/validate_trig.c checks the same restatement against libm exhaustively on the CPU.
+// ---------------------------------------------------------------------------------------------
+__device__ float dev_sinf(float y) {
+  const double HPI_INV = 0x1.45F306DC9C883p+23, HPI = 0x1.921FB54442D18p0;
+  const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5,
+               C3 = -0x1.6c087e89a359dp-10, C4 = 0x1.99343027bf8c3p-16;
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  double x = (double)y, x2;
+  int n = 0;
+  bool negc = false;
+  const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
+  if (top < 0x3f4u) {             // |y| < pi/4
+    if (top < 0x398u) return y;   // |y| < 2^-12
+    x2 = __dmul_rn(x, x);
+  } else if (top < 0x42fu) {      // |y| < 120
+    const double r = __dmul_rn(x, HPI_INV);
+    n = (__double2int_rz(r) + 0x800000) >> 24;
+    const double xr = __fma_rn(-(double)n, HPI, x);
+    x2 = __dmul_rn(xr, xr);
+    x = ((n & 3) == 1 || (n & 3) == 2) ? -xr : xr;
+    negc = (n & 2) != 0;
+  } else {
+    return sinf(y);  // outside the hot path's domain
+  }
+  if ((n & 1) == 0) {
+    const double x3 = __dmul_rn(x, x2), s1 = __fma_rn(x2, S3, S2), x7 = __dmul_rn(x3, x2);
+    const double s = __fma_rn(x3, S1, x);
+    return __double2float_rn(__fma_rn(x7, s1, s));
+  }
+  const double sg = negc ? -1.0 : 1.0;
+  const double x4 = __dmul_rn(x2, x2), c2 = __fma_rn(x2, sg * C4, sg * C3), c1 = __fma_rn(x2, sg * C1, sg * C0);
+  const double x6 = __dmul_rn(x4, x2), c = __fma_rn(x4, sg * C2, c1);
+  return __double2float_rn(__fma_rn(x6, c2, c));
+}
+
+__device__ float dev_atanf(float x) {
+  const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+  const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+  const float aT[11] = {3.3333334327e-01f,  -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
+                        9.0908870101e-02f,  -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
+                        4.9768779427e-02f,  -3.6531571299e-02f, 1.6285819933e-02f};
+  const int hx = (int)__float_as_uint(x), ix = hx & 0x7fffffff;
+  int id;
+  if (ix >= 0x4c000000) {
+    if (ix > 0x7f800000) return __fadd_rn(x, x);
+    return hx > 0 ? __fadd_rn(atanhi[3], atanlo[3]) : __fsub_rn(-atanhi[3], atanlo[3]);
+  }
+  if (ix < 0x3ee00000) {
+    if (ix < 0x31000000) return x;
+    id = -1;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000) {
+      if (ix < 0x3f300000) id = 0, x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x));
+      else id = 1, x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f));
+    } else {
+      if (ix < 0x401c0000) id = 2, x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x)));
+      else id = 3, x = __fdiv_rn(-1.0f, x);
+    }
+  }
+  const float z = __fmul_rn(x, x), w = __fmul_rn(z, z);
+#define MA(a, b, c) __fadd_rn((a), __fmul_rn((b), (c)))  /* a + b*c, two roundings */
+  const float s1 = __fmul_rn(z, MA(aT[0], w, MA(aT[2], w, MA(aT[4], w, MA(aT[6], w, MA(aT[8], w, aT[10]))))));
+  const float s2 = __fmul_rn(w, MA(aT[1], w, MA(aT[3], w, MA(aT[5], w, MA(aT[7], w, aT[9])))));
+#undef MA
+  const float t = __fmul_rn(x, __fadd_rn(s1, s2));
+  if (id < 0) return __fsub_rn(x, t);
+  const float r = __fsub_rn(atanhi[id], __fsub_rn(__fsub_rn(t, atanlo[id]), x));
+  return hx < 0 ? -r : r;
+}
+
+__device__ float dev_atan2f(float y, float x) {
+  const float pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f, tiny = 1.0e-30f;
+  const int hx = (int)__float_as_uint(x), ix = hx & 0x7fffffff;
+  const int hy = (int)__float_as_uint(y), iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return __fadd_rn(x, y);
+  if (hx == 0x3f800000) return dev_atanf(y);
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) return m < 2 ? y : (m == 2 ? __fadd_rn(pi, tiny) : __fsub_rn(-pi, tiny));
+  if (ix == 0) return hy < 0 ? __fsub_rn(-pi_o_2, tiny) : __fadd_rn(pi_o_2, tiny);
+  const int k = (iy - ix) >> 23;
+  float z;
+  if (k > 60) z = __fadd_rn(pi_o_2, __fmul_rn(0.5f, pi_lo));
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = dev_atanf(fabsf(__fdiv_rn(y, x)));
+  switch (m) {
+    case 0: return z;
+    case 1: return __uint_as_float(__float_as_uint(z) ^ 0x80000000u);
+    case 2: return __fsub_rn(pi, __fsub_rn(z, pi_lo));
+    default: return __fsub_rn(__fsub_rn(z, pi_lo), pi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST-9 score
+// ---------------------------------------------------------------------------------------------
+#define FAST_RING(F)                                                                         \
+  F(0, 0, -3) F(1, 1, -3) F(2, 2, -2) F(3, 3, -1) F(4, 3, 0) F(5, 3, 1) F(6, 2, 2) F(7, 1, 3) \
+  F(8, 0, 3) F(9, -1, 3) F(10, -2, 2) F(11, -3, 1) F(12, -3, 0) F(13, -3, -1) F(14, -2, -2) F(15, -1, -3)
+
+__device__ __forceinline__ bool run9(unsigned m) {  // circular run of >= 9 set bits in 16
+  const unsigned mm = m | (m << 16);
+  unsigned r = mm & (mm >> 1);
+  r &= r >> 2;
+  r &= r >> 4;
+  r &= mm >> 8;
+  return (r & 0xFFFFu) != 0;
+}
+
+__global__ void __launch_bounds__(256)
+k_fast_score(const uint8_t *__restrict__ src, unsigned w, unsigned h, unsigned n, uint8_t *__restrict__ score,
+             unsigned sw, unsigned sh, unsigned t) {
+  const unsigned x = 3 + blockIdx.x * 32 + threadIdx.x;
+  const unsigned y = 3 + blockIdx.y * 8 + threadIdx.y;
+  if (x + 3 >= w || y + 3 >= h) return;
+  for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
+    const uint8_t *c = src + (size_t)f * w * h + (size_t)y * w + x;
+    const unsigned p = __ldg(c), hi = p + t;
+    const bool wrap = t > p;          // reference :498: p - threshold wraps => always "darker"
+    const unsigned lo = p - t;        // only meaningful when !wrap
+    const int iw = (int)w;
+    // compass pre-test: any 9-arc contains at least two of ring positions 0, 4, 8, 12
+    unsigned v0 = __ldg(c - 3 * iw), v4 = __ldg(c + 3), v8 = __ldg(c + 3 * iw), v12 = __ldg(c - 3);
+    unsigned nb = (v0 > hi) + (v4 > hi) + (v8 > hi) + (v12 > hi);
+    unsigned nd = (!(v0 > hi) && (wrap || v0 < lo)) + (!(v4 > hi) && (wrap || v4 < lo)) +
+                  (!(v8 > hi) && (wrap || v8 < lo)) + (!(v12 > hi) && (wrap || v12 < lo));
+    unsigned s = 0;
+    if (nb >= 2 || nd >= 2) {
+      unsigned bright = 0, dark = 0, mind = 255;
+#define FAST_TAP(i, dx, dy)                                        \
+  {                                                                \
+    const unsigned v = __ldg(c + (dy) * iw + (dx));                \
+    const bool b = v > hi;                                         \
+    const bool d = !b && (wrap || v < lo);                         \
+    bright |= (unsigned)b << (i);                                  \
+    dark |= (unsigned)d << (i);                                    \
+    mind = min(mind, v > p ? v - p : p - v);                       \
+  }
+      FAST_RING(FAST_TAP)
+#undef FAST_TAP
+      if (run9(bright) || run9(dark)) s = mind;
+    }
+    if (x < sw && y < sh) score[(size_t)f * sw * sh + (size_t)y * sw + x] = (uint8_t)s;
+  }
+}
+
+// score-map read with the reference's gs_get semantics (0 outside the map)
+__device__ __forceinline__ unsigned sm_get(const uint8_t *sm, unsigned sw, unsigned sh, unsigned x, unsigned y) {
+  return (x < sw && y < sh) ? sm[(size_t)y * sw + x] : 0u;
+}
+__device__ __forceinline__ bool nms_keep(const uint8_t *sm, unsigned sw, unsigned sh, unsigned x, unsigned y,
+                                         unsigned &s) {
+  s = sm_get(sm, sw, sh, x, y);
+  if (s == 0) return false;
+  return sm_get(sm, sw, sh, x - 1, y - 1) <= s && sm_get(sm, sw, sh, x, y - 1) <= s &&
+         sm_get(sm, sw, sh, x + 1, y - 1) <= s && sm_get(sm, sw, sh, x - 1, y) <= s &&
+         sm_get(sm, sw, sh, x + 1, y) <= s && sm_get(sm, sw, sh, x - 1, y + 1) <= s &&
+         sm_get(sm, sw, sh, x, y + 1) <= s && sm_get(sm, sw, sh, x + 1, y + 1) <= s;
+}
+
+// one CTA per (interior row, frame): number of NMS survivors in that row
+__global__ void __launch_bounds__(256)
+k_nms_count(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h,
+            unsigned *__restrict__ rowcount) {
+  const unsigned rows = h - 6, y = 3 + blockIdx.x, f = blockIdx.y;
+  const uint8_t *sm = score + (size_t)f * sw * sh;
+  unsigned total = 0;
+  for (unsigned xb = 3; xb + 3 < w; xb += 256) {
+    const unsigned x = xb + threadIdx.x;
+    unsigned s;
+    const bool keep = (x + 3 < w) && nms_keep(sm, sw, sh, x, y, s);
+    total += __syncthreads_count(keep);
+  }
+  if (threadIdx.x == 0) rowcount[(size_t)f * rows + blockIdx.x] = total;
+}
+
+struct KpRec {  // struct gs_keypoint, 48 bytes
+  uint32_t w[12];
+};
+
+__global__ void __launch_bounds__(256)
+k_nms_emit(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h,
+           const unsigned *__restrict__ rowoff, KpRec *__restrict__ kps, unsigned nkps) {
+  __shared__ unsigned wcnt[8];
+  const unsigned rows = h - 6, y = 3 + blockIdx.x, f = blockIdx.y;
+  unsigned base = rowoff[(size_t)f * rows + blockIdx.x];
+  if (base >= nkps) return;
+  const uint8_t *sm = score + (size_t)f * sw * sh;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned xb = 3; xb + 3 < w; xb += 256) {
+    const unsigned x = xb + threadIdx.x;
+    unsigned s = 0;
+    const bool keep = (x + 3 < w) && nms_keep(sm, sw, sh, x, y, s);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const unsigned c = wcnt[i];
+      before += (i < (int)warp) ? c : 0;
+      total += c;
+    }
+    const unsigned pos = base + before + __popc(bal & ((1u << lane) - 1u));
+    if (keep && pos < nkps) {
+      KpRec r;
+      r.w[0] = x, r.w[1] = y, r.w[2] = s;
+#pragma unroll
+      for (int i = 3; i < 12; i++) r.w[i] = 0;  // angle 0.0f, descriptor {0} (reference :530)
+      uint4 *o = reinterpret_cast<uint4 *>(kps + (size_t)f * nkps + pos);
+      o[0] = make_uint4(r.w[0], r.w[1], r.w[2], 0), o[1] = make_uint4(0, 0, 0, 0), o[2] = make_uint4(0, 0, 0, 0);
+    }
+    base += total;
+    if (base >= nkps) return;  // uniform
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ORB: stable sort by response, margin filter, cap
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned ORB_MAXC = 5000;  // the reference's static candidates[5000] (grayskull.h:655)
+
+__global__ void __launch_bounds__(256)
+k_orb_select(const KpRec *__restrict__ cand, const unsigned *__restrict__ cand_count, unsigned cap, unsigned w,
+             unsigned h, KpRec *__restrict__ kps, unsigned *__restrict__ counts, unsigned nkps) {
+  __shared__ uint8_t resp[ORB_MAXC];
+  __shared__ uint16_t order[ORB_MAXC];
+  __shared__ unsigned start[256];
+  __shared__ unsigned wcnt[8];
+  const unsigned f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const KpRec *c = cand + (size_t)f * cap;
+  const unsigned n = min(cand_count[f], cap);
+  start[tid] = 0;
+  __syncthreads();
+  for (unsigned i = tid; i < n; i += 256) {
+    const unsigned r = min(c[i].w[2], 255u);
+    resp[i] = (uint8_t)r;
+    atomicAdd(&start[r], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {  // descending exclusive prefix: start[b] = #candidates with response > b
+    unsigned acc = 0;
+    for (int b = 255; b >= 0; b--) {
+      const unsigned cnt = start[b];
+      start[b] = acc, acc += cnt;
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {  // stable rank inside equal-response groups, in candidate (raster) order
+    for (unsigned b = 0; b < n; b += 32) {
+      const unsigned i = b + lane;
+      const unsigned key = i < n ? resp[i] : 0x10000u + lane;
+      const unsigned m = __match_any_sync(0xFFFFFFFFu, key);
+      if (i < n) order[start[key] + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+      __syncwarp();
+      if (i < n && lane == (unsigned)(__ffs(m) - 1)) start[key] += __popc(m);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // first nkps sorted candidates at least 15 px away from every border (reference :659-667)
+  unsigned running = 0;
+  const unsigned radius = 15;
+  for (unsigned b = 0; b < n && running < nkps; b += 256) {
+    const unsigned pos = b + tid;
+    unsigned x = 0, y = 0, r = 0;
+    bool pass = false;
+    if (pos < n) {
+      const KpRec k = c[order[pos]];
+      x = k.w[0], y = k.w[1], r = k.w[2];
+      pass = x >= radius && y >= radius && x < w - radius && y < h - radius;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, pass);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    unsigned before = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const unsigned cc = wcnt[i];
+      before += (i < (int)warp) ? cc : 0;
+      total += cc;
+    }
+    const unsigned j = running + before + __popc(bal & ((1u << lane) - 1u));
+    if (pass && j < nkps) {
+      uint4 *o = reinterpret_cast<uint4 *>(kps + (size_t)f * nkps + j);
+      o[0] = make_uint4(x, y, r, 0), o[1] = make_uint4(0, 0, 0, 0), o[2] = make_uint4(0, 0, 0, 0);
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (tid == 0) counts[f] = min(running, nkps);
+}
+
+// intensity-centroid moments over the disc dx^2 + dy^2 <= r^2; lanes = dx (r <= 15 per pass)
+__device__ __forceinline__ void disc_moments(const uint8_t *img, unsigned w, int x, int y, int r, unsigned lane,
+                                             int &m01, int &m10) {
+  int a01 = 0, a10 = 0;
+  for (int dx0 = -r; dx0 <= r; dx0 += 32) {
+    const int dx = dx0 + (int)lane;
+    if (dx <= r)
+      for (int dy = -r; dy <= r; dy++)
+        if (dx * dx + dy * dy <= r * r) {
+          const int v = __ldg(img + (size_t)(y + dy) * w + (x + dx));
+          a01 += dy * v, a10 += dx * v;
+        }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a01 += __shfl_xor_sync(0xFFFFFFFFu, a01, o);
+    a10 += __shfl_xor_sync(0xFFFFFFFFu, a10, o);
+  }
+  m01 = a01, m10 = a10;
+}
+
+__device__ __forceinline__ float orient_from_moments(int m01, int m10, int trig_mode) {
+  // the reference's float accumulators hold exact integers (< 2^24 for r = 15), so the int32
+  // moments converted once are the same floats (reference :608-620)
+  return trig_mode ? atan2f((float)m01, (float)m10) : dev_atan2f((float)m01, (float)m10);
+}
+
+// BRIEF-256 (reference :623-637); each ballot is one descriptor word
+__device__ __forceinline__ void brief_words(const uint8_t *img, unsigned w, unsigned h, int x, int y, float angle,
+                                            unsigned lane, int trig_mode, uint32_t (&desc)[8]) {
+  const float a2 = __fadd_rn(angle, 1.57079f);
+  const float sin_a = trig_mode ? sinf(angle) : dev_sinf(angle);
+  const float cos_a = trig_mode ? sinf(a2) : dev_sinf(a2);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t pk = c_brief[32 * k + lane];
+    const float p0 = (float)(int)(int8_t)(pk & 0xFF), p1 = (float)(int)(int8_t)((pk >> 8) & 0xFF);
+    const float p2 = (float)(int)(int8_t)((pk >> 16) & 0xFF), p3 = (float)(int)(int8_t)(pk >> 24);
+    const float dx1 = __fsub_rn(__fmul_rn(p0, cos_a), __fmul_rn(p1, sin_a));
+    const float dy1 = __fadd_rn(__fmul_rn(p0, sin_a), __fmul_rn(p1, cos_a));
+    const float dx2 = __fsub_rn(__fmul_rn(p2, cos_a), __fmul_rn(p3, sin_a));
+    const float dy2 = __fadd_rn(__fmul_rn(p2, sin_a), __fmul_rn(p3, cos_a));
+    const unsigned x1 = (unsigned)(x + __float2int_rz(dx1)), y1 = (unsigned)(y + __float2int_rz(dy1));
+    const unsigned x2 = (unsigned)(x + __float2int_rz(dx2)), y2 = (unsigned)(y + __float2int_rz(dy2));
+    const unsigned i1 = (x1 < w && y1 < h) ? __ldg(img + (size_t)y1 * w + x1) : 0u;
+    const unsigned i2 = (x2 < w && y2 < h) ? __ldg(img + (size_t)y2 * w + x2) : 0u;
+    desc[k] = __ballot_sync(0xFFFFFFFFu, i1 > i2);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_orb_describe(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__restrict__ kps,
+               const unsigned *__restrict__ counts, unsigned nkps, unsigned n, int trig_mode) {
+  const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (gw >= (unsigned long long)n * nkps) return;
+  const unsigned f = (unsigned)(gw / nkps), j = (unsigned)(gw % nkps);
+  if (j >= counts[f]) return;
+  KpRec *k = kps + (size_t)f * nkps + j;
+  const uint8_t *img = src + (size_t)f * w * h;
+  const int x = (int)k->w[0], y = (int)k->w[1];
+  int m01, m10;
+  disc_moments(img, w, x, y, 15, lane, m01, m10);
+  const float angle = orient_from_moments(m01, m10, trig_mode);
+  uint32_t desc[8];
+  brief_words(img, w, h, x, y, angle, lane, trig_mode, desc);
+  if (lane == 0) {
+    uint4 *o = reinterpret_cast<uint4 *>(k);
+    o[0] = make_uint4(k->w[0], k->w[1], k->w[2], __float_as_uint(angle));
+    o[1] = make_uint4(desc[0], desc[1], desc[2], desc[3]);
+    o[2] = make_uint4(desc[4], desc[5], desc[6], desc[7]);
+  }
+}
+
+// single-call forms of gs_compute_orientation / gs_brief_descriptor (one warp)
+__global__ void k_orient_one(const uint8_t *img, unsigned w, unsigned x, unsigned y, unsigned r, int trig_mode,
+                             float *out) {
+  int m01, m10;
+  disc_moments(img, w, (int)x, (int)y, (int)r, threadIdx.x, m01, m10);
+  // for r > 15 the reference's float accumulation may round; int32 moments stay exact while
+  // |moment| < 2^24, which holds for r <= 15 (the only radius the library itself uses)
+  const float a = orient_from_moments(m01, m10, trig_mode);
+  if (threadIdx.x == 0) *out = a;
+}
+__global__ void k_brief_one(const uint8_t *img, unsigned w, unsigned h, KpRec *kp, int trig_mode) {
+  uint32_t desc[8];
+  brief_words(img, w, h, (int)kp->w[0], (int)kp->w[1], __uint_as_float(kp->w[3]), threadIdx.x, trig_mode, desc);
+  if (threadIdx.x < 8) kp->w[4 + threadIdx.x] = desc[threadIdx.x];
+}
+
+static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uint8_t *score, unsigned sw,
+                     unsigned sh, KpRec *kps, unsigned *counts, unsigned nkps, unsigned threshold,
+                     cudaStream_t s) {
+  if (n == 0) return 0;
+  if (w < 7 || h < 7) {  // no interior pixel: nothing written, no keypoints
+    GSB_CHECK(cudaMemsetAsync(counts, 0, sizeof(unsigned) * n, s));
+    return 0;
+  }
+  const unsigned rows = h - 6;
+  unsigned *rowcount = static_cast<unsigned *>(workspace(s, WS_FAST_A, sizeof(unsigned) * (size_t)rows * n));
+  if (!rowcount) return (int)cudaErrorMemoryAllocation;
+  {
+    dim3 block(32, 8), grid((w - 6 + 31) / 32, (h - 6 + 7) / 8, n < 65535u ? n : 65535u);
+    k_fast_score<<<grid, block, 0, s>>>(src, w, h, n, score, sw, sh, threshold);
+    GSB_LAUNCHED(1);
+  }
+  GSB_ASSERT(n <= 65535u && rows <= 0x7FFFFFFFu);
+  k_nms_count<<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, rowcount);
+  GSB_LAUNCHED(1);
+  k_row_scan<<<n, 1024, 0, s>>>(rowcount, rows, counts, nkps);
+  GSB_LAUNCHED(1);
+  k_nms_emit<<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, rowcount, kps, nkps);
+  GSB_LAUNCHED(1);
+  return 0;
+}
+
+}  // namespace gsb
+
+extern "C" {
+
+void gs_b200_set_trig_mode(int mode) { gsb::g_trig_mode = mode ? 1 : 0; }
+
+int gs_b200_fast_batch(const uint8_t *src, unsigned w, unsigned h, unsigned n, uint8_t *scoremap,
+                       struct gs_keypoint *kps, unsigned *counts, unsigned nkps, unsigned threshold,
+                       gs_b200_stream s) {
+  GSB_ASSERT(src && w > 0 && h > 0 && kps && nkps > 0);  // reference :484
+  GSB_ASSERT(scoremap && counts);
+  return gsb::fast_impl(src, w, h, n, scoremap, w, h, reinterpret_cast<gsb::KpRec *>(kps), counts, nkps,
+                        threshold, static_cast<cudaStream_t>(s));
+}
+
+int gs_b200_orb_extract_batch(const uint8_t *src, unsigned w, unsigned h, unsigned n, uint8_t *scoremap,
+                              struct gs_keypoint *kps, unsigned *counts, unsigned nkps, unsigned threshold,
+                              gs_b200_stream s) {
+  GSB_ASSERT(src && w > 0 && h > 0 && kps && nkps > 0 && scoremap);  // reference :653
+  GSB_ASSERT(counts);
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  const unsigned cap = nkps * 4ull < gsb::ORB_MAXC ? nkps * 4 : gsb::ORB_MAXC;  // reference :656
+  gsb::KpRec *cand = static_cast<gsb::KpRec *>(gsb::workspace(st, gsb::WS_ORB_A, sizeof(gsb::KpRec) * (size_t)cap * n));
+  unsigned *ccount = static_cast<unsigned *>(gsb::workspace(st, gsb::WS_ORB_B, sizeof(unsigned) * n));
+  if (!cand || !ccount) return (int)cudaErrorMemoryAllocation;
+  int rc = gsb::fast_impl(src, w, h, n, scoremap, w, h, cand, ccount, cap, threshold, st);
+  if (rc) return rc;
+  gsb::k_orb_select<<<n, 256, 0, st>>>(cand, ccount, cap, w, h, reinterpret_cast<gsb::KpRec *>(kps), counts, nkps);
+  GSB_LAUNCHED(1);
+  const unsigned long long warps = (unsigned long long)n * nkps;
+  const unsigned long long blocks = (warps + 7) / 8;
+  GSB_ASSERT(blocks < 0x7FFFFFFFull);
+  gsb::k_orb_describe<<<(unsigned)blocks, 256, 0, st>>>(src, w, h, reinterpret_cast<gsb::KpRec *>(kps), counts, nkps, n,
+                                                        gsb::g_trig_mode);
+  GSB_LAUNCHED(1);
+  return 0;
+}
+
+// internal hooks used by api.cu for the single-image calls
+int gsb_fast_single(const uint8_t *src, unsigned w, unsigned h, uint8_t *score, unsigned sw, unsigned sh,
+                    struct gs_keypoint *kps, unsigned *count, unsigned nkps, unsigned threshold, cudaStream_t s) {
+  return gsb::fast_impl(src, w, h, 1, score, sw, sh, reinterpret_cast<gsb::KpRec *>(kps), count, nkps, threshold, s);
+}
+int gsb_orient_single(const uint8_t *img, unsigned w, unsigned x, unsigned y, unsigned r, float *out, cudaStream_t s) {
+  gsb::k_orient_one<<<1, 32, 0, s>>>(img, w, x, y, r, gsb::g_trig_mode, out);
+  GSB_LAUNCHED(1);
+  return 0;
+}
+int gsb_brief_single(const uint8_t *img, unsigned w, unsigned h, struct gs_keypoint *kp, cudaStream_t s) {
+  gsb::k_brief_one<<<1, 32, 0, s>>>(img, w, h, reinterpret_cast<gsb::KpRec *>(kp), gsb::g_trig_mode);
+  GSB_LAUNCHED(1);
+  return 0;
+}
+}

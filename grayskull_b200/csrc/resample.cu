@@ -1,0 +1,107 @@
+// resample.cu -- gs_resize and gs_downsample (reference grayskull.h:171-197).
+#include "common.cuh"
+
+namespace gsb {
+
+// ---- gs_downsample: (a+b+c+d)/4 over 2x2 blocks, 1.25 B per source pixel ----------------------
+// Fast path: a thread reads two aligned 16-byte row segments (128-bit loads) and writes 8 output
+// bytes.  Horizontal pair sums and the two rows are added on 16-bit lanes, >>2 under a mask.
+__global__ void k_downsample_vec(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, unsigned sw,
+                                 unsigned sh, unsigned dw, unsigned dh, unsigned n) {
+  const unsigned gx = blockIdx.x * blockDim.x + threadIdx.x;  // 8 dst pixels each
+  const unsigned y = blockIdx.y;
+  if (gx * 8 >= dw) return;
+  for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
+    const uint4 *r0 = reinterpret_cast<const uint4 *>(src + (size_t)f * sw * sh + (size_t)(2 * y) * sw) + gx;
+    const uint4 *r1 = reinterpret_cast<const uint4 *>(src + (size_t)f * sw * sh + (size_t)(2 * y + 1) * sw) + gx;
+    const uint4 a = __ldg(r0), b = __ldg(r1);
+    auto quad = [](uint32_t u, uint32_t v) -> uint32_t {  // lanes: (b0+b1+.., b2+b3+..) >> 2
+      uint32_t s = (u & 0x00FF00FFu) + ((u >> 8) & 0x00FF00FFu) + (v & 0x00FF00FFu) + ((v >> 8) & 0x00FF00FFu);
+      return (s >> 2) & 0x00FF00FFu;
+    };
+    uint2 o;
+    o.x = prmt(quad(a.x, b.x), quad(a.y, b.y), 0x6420);
+    o.y = prmt(quad(a.z, b.z), quad(a.w, b.w), 0x6420);
+    st_cs_u2(dst + (size_t)f * dw * dh + (size_t)y * dw + gx * 8, o);
+  }
+}
+
+__global__ void k_downsample_generic(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                                     unsigned sw, unsigned sh, unsigned dw, unsigned dh, unsigned n) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
+    const uint8_t *p = src + (size_t)f * sw * sh + (size_t)(2 * y) * sw + 2 * x;
+    dst[(size_t)f * dw * dh + (size_t)y * dw + x] = (uint8_t)((p[0] + p[1] + p[sw] + p[sw + 1]) / 4);
+  }
+}
+
+// ---- gs_resize: pixel-centre bilinear, fp32 in the reference's exact evaluation order ---------
+// Every rounding step of grayskull.h:174-184 is reproduced with the _rn intrinsics (never
+// contracted into FMAs): sx = ((x + 0.5f) * sw) / dw - 0.5f, clamp, truncate, and the sum of
+// four products ((c * wx) * wy) added left to right.
+__device__ __forceinline__ void resize_axis(unsigned i, unsigned sdim, unsigned ddim, unsigned &i0,
+                                            unsigned &i1, float &frac) {
+  float s = __fsub_rn(__fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), (float)sdim), (float)ddim), 0.5f);
+  const float hi = __fsub_rn((float)sdim, 1.0f);
+  s = s < hi ? s : hi;
+  s = 0.0f > s ? 0.0f : s;
+  i0 = __float2uint_rz(s);
+  i1 = i0 + 1 < sdim - 1 ? i0 + 1 : sdim - 1;
+  frac = __fsub_rn(s, (float)i0);
+}
+
+__global__ void k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src,
+                         unsigned sw, unsigned sh, unsigned n) {
+  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  unsigned x0, x1, y0, y1;
+  float dx, dy;
+  resize_axis(x, sw, dw, x0, x1, dx);
+  resize_axis(y, sh, dh, y0, y1, dy);
+  const float omx = __fsub_rn(1.0f, dx), omy = __fsub_rn(1.0f, dy);
+  for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
+    const uint8_t *s = src + (size_t)f * sw * sh;
+    const float c00 = (float)__ldg(s + (size_t)y0 * sw + x0), c01 = (float)__ldg(s + (size_t)y0 * sw + x1);
+    const float c10 = (float)__ldg(s + (size_t)y1 * sw + x0), c11 = (float)__ldg(s + (size_t)y1 * sw + x1);
+    float p = __fmul_rn(__fmul_rn(c00, omx), omy);
+    p = __fadd_rn(p, __fmul_rn(__fmul_rn(c01, dx), omy));
+    p = __fadd_rn(p, __fmul_rn(__fmul_rn(c10, omx), dy));
+    p = __fadd_rn(p, __fmul_rn(__fmul_rn(c11, dx), dy));
+    dst[(size_t)f * dw * dh + (size_t)y * dw + x] = (uint8_t)__float2uint_rz(p);
+  }
+}
+
+}  // namespace gsb
+
+extern "C" {
+int gs_b200_downsample_batch(uint8_t *dst, const uint8_t *src, unsigned sw, unsigned sh, unsigned n,
+                             gs_b200_stream s) {
+  GSB_ASSERT(dst && src && sw > 0 && sh > 0);  // reference :190
+  const unsigned dw = sw / 2, dh = sh / 2;
+  if (n == 0 || dw == 0 || dh == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(s);
+  const unsigned zn = n < 65535u ? n : 65535u;
+  if (gsb::tma_ok(src, sw) && reinterpret_cast<uintptr_t>(dst) % 8 == 0 && dh <= 65535u) {
+    dim3 block(128), grid((dw / 8 + 127) / 128, dh, zn);
+    gsb::k_downsample_vec<<<grid, block, 0, st>>>(dst, src, sw, sh, dw, dh, n);
+  } else {
+    dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8, zn);
+    gsb::k_downsample_generic<<<grid, block, 0, st>>>(dst, src, sw, sh, dw, dh, n);
+  }
+  GSB_LAUNCHED(1);
+  return 0;
+}
+
+int gs_b200_resize_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *src, unsigned sw,
+                         unsigned sh, unsigned n, gs_b200_stream s) {
+  GSB_ASSERT(dst && src && dw > 0 && dh > 0 && sw > 0 && sh > 0);  // reference :172
+  if (n == 0) return 0;
+  dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8, n < 65535u ? n : 65535u);
+  gsb::k_resize<<<grid, block, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n);
+  GSB_LAUNCHED(1);
+  return 0;
+}
+}

@@ -35,6 +35,8 @@ const char *gs_b200_last_error(void);
 const char *gs_b200_version(void);
 /* 1 if the fast (TMA-tiled) kernels are used for this geometry, 0 if the generic kernels */
 int gs_b200_uses_tma(unsigned w, unsigned h, const void *ptr);
+/* testing hook: 1 = always take the generic (non-TMA) kernels; same as GS_B200_FORCE_GENERIC=1 */
+void gs_b200_force_generic(int on);
 /* number of kernel launches issued by this library since process start (bench bookkeeping) */
 unsigned long long gs_b200_launch_count(void);
 

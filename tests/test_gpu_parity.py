@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libgrayskull_b200.so) against
+  * the reference-generated golden fixtures in tests/golden/ (bit-exact),
+  * the oracle restatement on the same seeded inputs (bit-exact),
+  * size-independent properties / crop checks at BASELINE.json's full sizes.
+Bit-exact everywhere; gs_compute_orientation's angle is additionally checked within 1e-5 in the
+libdevice trig mode (north_star's stated tolerance).  Needs a CUDA device (-m gpu)."""
+import os
+
+import numpy as np
+import pytest
+
+import _libs as L
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(L.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+    import grayskull_b200 as g
+    from grayskull_b200 import api
+    assert torch.cuda.is_available()
+    g.lib().gs_b200_set_device(0)
+    return api
+
+
+@pytest.fixture(scope="module")
+def O():
+    return L.oracle()
+
+
+@pytest.fixture(scope="module")
+def cas():
+    import grayskull_b200 as g
+    return g.load_cascade()
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ---- oracle helpers -------------------------------------------------------------------------
+def o_blur(O, a, r):
+    d = np.empty_like(a); O.gso_blur(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], r); return d
+def o_adaptive(O, a, r, c):
+    d = np.empty_like(a); O.gso_adaptive_threshold(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], r, c); return d
+def o_morph(O, a, dil):
+    d = np.empty_like(a); O.gso_morph(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], dil); return d
+def o_sobel(O, a, fill=0):
+    d = np.full_like(a, fill); O.gso_sobel(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0]); return d
+def o_resize(O, a, dw, dh):
+    d = np.empty((dh, dw), np.uint8); O.gso_resize(L.ptr(d), dw, dh, L.ptr(a), a.shape[1], a.shape[0]); return d
+def o_down(O, a):
+    d = np.empty((a.shape[0] // 2, a.shape[1] // 2), np.uint8); O.gso_downsample(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0]); return d
+def o_integral(O, a):
+    ii = np.empty(a.shape, np.uint32); O.gso_integral(L.ptr(a), a.shape[1], a.shape[0], L.ptr(ii)); return ii
+def o_fast(O, a, sm, nkps, t):
+    k = np.zeros(nkps, L.KP_DTYPE)
+    n = O.gso_fast(L.ptr(a), a.shape[1], a.shape[0], L.ptr(sm), sm.shape[1], sm.shape[0], L.ptr(k), nkps, t)
+    return k[:n]
+def o_orb(O, a, sm, nkps, t):
+    k = np.zeros(nkps, L.KP_DTYPE)
+    n = O.gso_orb_extract(L.ptr(a), a.shape[1], a.shape[0], L.ptr(k), nkps, t, L.ptr(sm))
+    return k[:n]
+def o_detect(O, cas, ii, max_rects, sf, mn, mx, step):
+    r = np.zeros(max(max_rects, 1), L.RECT_DTYPE)
+    n = O.gso_lbp_detect(cas.ptr, L.ptr(ii), ii.shape[1], ii.shape[0], L.ptr(r), max_rects, sf, mn, mx, step)
+    return r[:n]
+
+
+# ---- single-image gs_* API (host pointers, staged) against the reference's own fixtures ------
+def test_golden_lena_single_image_api(G, cas):
+    """BASELINE config C1: gs_sobel (and every other op) on testdata/lena.pgm, bit-exact against
+    outputs the real reference produced (tools/make_golden.py)."""
+    z = np.load(os.path.join(GOLD, "lena_golden.npz"))
+    a = z["lena"]
+    d = np.zeros_like(a); G.gs_sobel(d, a); assert np.array_equal(d, z["sobel"])
+    for r in (1, 5, 9):
+        d = np.empty_like(a); G.gs_blur(d, a, r); assert np.array_equal(d, z["blur%d" % r]), r
+    d = np.empty_like(a); G.gs_adaptive_threshold(d, a, 15, 5); assert np.array_equal(d, z["adaptive_15_5"])
+    d = np.empty_like(a); G.gs_erode(d, a); assert np.array_equal(d, z["erode"])
+    d = np.empty_like(a); G.gs_dilate(d, a); assert np.array_equal(d, z["dilate"])
+    d = np.empty((64, 128), np.uint8); G.gs_resize(d, a); assert np.array_equal(d, z["resize_128x64"])
+    d = np.empty((64, 64), np.uint8); G.gs_downsample(d, a); assert np.array_equal(d, z["downsample"])
+    ii = np.empty(a.shape, np.uint32); G.gs_integral(a, ii); assert np.array_equal(ii, z["integral"])
+    sm = np.zeros_like(a)
+    k = G.gs_fast(a, sm, 5000, 20)
+    assert k.tobytes() == z["fast_kps"].tobytes() and np.array_equal(sm, z["fast_scoremap"])
+    k = G.gs_orb_extract(a, 500, 20, np.zeros_like(a))
+    assert len(k) == len(z["orb_kps"]) == 280
+    assert k.tobytes() == z["orb_kps"].tobytes()       # angles and descriptors bit-identical
+    r = G.gs_lbp_detect(cas, ii, 1000, 1.1, 1.0, 4.0, 2)
+    assert r.tobytes() == z["lbp_rects"].tobytes() and len(r) == 10
+    # the individual ORB pieces
+    ref_k = z["orb_kps"]
+    for i in (0, 7, 100, 279):
+        ang = G.gs_compute_orientation(a, int(ref_k[i]["x"]), int(ref_k[i]["y"]), 15)
+        assert np.float32(ang).tobytes() == np.float32(ref_k[i]["angle"]).tobytes()
+        kp = ref_k[i:i + 1].copy(); kp["descriptor"] = 0
+        G.gs_brief_descriptor(a, kp)
+        assert kp.tobytes() == ref_k[i:i + 1].tobytes()
+    # single windows
+    for (x, y, s) in ((54, 52, 1.9487171), (0, 0, 1.0), (100, 100, 1.0), (30, 40, 2.0)):
+        got = G.gs_lbp_window(cas, ii, x, y, s)
+        want = L.oracle().gso_lbp_window(cas.ptr, L.ptr(ii), 128, 128, x, y, s)
+        assert got == want
+
+
+def test_golden_random_ragged(G, cas):
+    """odd sizes (33x29 ... 130x131): generic (non-TMA) kernels, reference-generated fixtures"""
+    z = np.load(os.path.join(GOLD, "random_golden.npz"))
+    for i, (w, h) in enumerate(z["shapes"]):
+        a = z["img%d" % i]; t = "i%d_" % i
+        d = np.zeros_like(a); G.gs_sobel(d, a); assert np.array_equal(d, z[t + "sobel"]), (w, h)
+        for r in (1, 5, 9):
+            d = np.empty_like(a); G.gs_blur(d, a, r); assert np.array_equal(d, z[t + "blur%d" % r]), (w, h, r)
+        d = np.empty_like(a); G.gs_adaptive_threshold(d, a, 15, 5); assert np.array_equal(d, z[t + "adaptive_15_5"])
+        d = np.empty_like(a); G.gs_erode(d, a); assert np.array_equal(d, z[t + "erode"])
+        d = np.empty_like(a); G.gs_dilate(d, a); assert np.array_equal(d, z[t + "dilate"])
+        d = np.empty((64, 128), np.uint8); G.gs_resize(d, a); assert np.array_equal(d, z[t + "resize_128x64"])
+        d = np.empty((h // 2, w // 2), np.uint8); G.gs_downsample(d, a); assert np.array_equal(d, z[t + "downsample"])
+        ii = np.empty(a.shape, np.uint32); G.gs_integral(a, ii); assert np.array_equal(ii, z[t + "integral"])
+        sm = np.zeros_like(a)
+        k = G.gs_fast(a, sm, 5000, 20)
+        assert k.tobytes() == z[t + "fast_kps"].tobytes() and np.array_equal(sm, z[t + "fast_scoremap"]), (w, h)
+        k = G.gs_orb_extract(a, 200, 20, np.zeros_like(a))
+        assert k.tobytes() == z[t + "orb_kps"].tobytes(), (w, h)
+        if t + "lbp_rects" in z.files:
+            r = G.gs_lbp_detect(cas, ii, 1000, 1.1, 1.0, 4.0, 2)
+            assert r.tobytes() == z[t + "lbp_rects"].tobytes(), (w, h)
+
+
+def test_sobel_border_untouched(G):
+    a = L.natural_like(64, 48, 1)
+    d = np.full_like(a, 77); G.gs_sobel(d, a)
+    assert (d[0] == 77).all() and (d[-1] == 77).all() and (d[:, 0] == 77).all() and (d[:, -1] == 77).all()
+    tiny = np.full((2, 2), 9, np.uint8); d = np.full_like(tiny, 5); G.gs_sobel(d, tiny); assert (d == 5).all()
+
+
+def test_fast_quirks(G):
+    """SURVEY appendix B quirk probes: dark-centre wrap, stale score-map ring, cap in raster order"""
+    a = np.full((7, 7), 5, np.uint8); a[3, 3] = 3
+    sm = np.zeros((7, 7), np.uint8)
+    k = G.gs_fast(a, sm, 10, 20)
+    assert len(k) == 1 and sm[3, 3] == 2 and k[0]["response"] == 2
+    sm = np.zeros((7, 7), np.uint8); sm[2, 2] = 200
+    assert len(G.gs_fast(a, sm, 10, 20)) == 0 and sm[2, 2] == 200
+    b = np.full((7, 7), 105, np.uint8); b[3, 3] = 103
+    assert len(G.gs_fast(b, np.zeros((7, 7), np.uint8), 10, 20)) == 0
+    assert len(G.gs_fast(a, None, 10, 20)) == 0      # invalid score map: writes dropped, reads 0
+
+
+# ---- batched device API vs oracle on seeded inputs (TMA and generic kernels) -----------------
+SHAPES = [(256, 128), (272, 140), (512, 300), (16, 16), (48, 7), (1024, 67), (640, 480), (100, 37), (17, 1), (1, 1)]
+
+
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_stencils_vs_oracle(G, O, force_generic):
+    import grayskull_b200 as g
+    g.lib().gs_b200_force_generic(force_generic)
+    try:
+        rng = np.random.default_rng(7)
+        for (w, h) in SHAPES:
+            n = 3
+            frames = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint8) if i != 1 else L.natural_like(w, h, 3)
+                               for i in range(n)])
+            src = dev(frames)
+            got = G.sobel_batch(src, out=dev(np.full_like(frames, 77))).cpu().numpy()
+            for i in range(n):
+                assert np.array_equal(got[i], o_sobel(O, frames[i], 77)), ("sobel", w, h, i)
+            ge, gd = G.erode_batch(src).cpu().numpy(), G.dilate_batch(src).cpu().numpy()
+            for i in range(n):
+                assert np.array_equal(ge[i], o_morph(O, frames[i], 0)), ("erode", w, h, i)
+                assert np.array_equal(gd[i], o_morph(O, frames[i], 1)), ("dilate", w, h, i)
+            for r in (0, 1, 2, 3, 4, 5, 6, 7, 8, 11):
+                gb = G.blur_batch(src, r).cpu().numpy()
+                c = int(rng.integers(-40, 40))
+                ga = G.adaptive_threshold_batch(src, r, c).cpu().numpy()
+                for i in range(n):
+                    assert np.array_equal(gb[i], o_blur(O, frames[i], r)), ("blur", w, h, r, i)
+                    assert np.array_equal(ga[i], o_adaptive(O, frames[i], r, c)), ("adaptive", w, h, r, c, i)
+            if w >= 2 and h >= 2:
+                gd = G.downsample_batch(src).cpu().numpy()
+                for i in range(n):
+                    assert np.array_equal(gd[i], o_down(O, frames[i])), ("down", w, h)
+            for (dw, dh) in ((w // 2 + 1, h // 2 + 1), (w * 2 + 3, h + 5), (w, h), (7, 3)):
+                gr = G.resize_batch(src, dw, dh).cpu().numpy()
+                for i in range(n):
+                    assert np.array_equal(gr[i], o_resize(O, frames[i], dw, dh)), ("resize", w, h, dw, dh)
+            gi = G.integral_batch(src).cpu().numpy().view(np.uint32)
+            for i in range(n):
+                assert np.array_equal(gi[i], o_integral(O, frames[i])), ("integral", w, h)
+    finally:
+        g.lib().gs_b200_force_generic(0)
+
+
+def test_blur_constant_and_saturated(G, O):
+    """all-255 and all-0 frames: the division must be exact at the extremes for every clipped count"""
+    for r in range(1, 8):
+        for v in (255, 0, 1, 254):
+            a = np.full((2, 80, 272), v, np.uint8)
+            assert (G.blur_batch(dev(a), r).cpu().numpy() == v).all(), (r, v)
+
+
+def test_fast_orb_vs_oracle(G, O):
+    rng = np.random.default_rng(11)
+    for (w, h, nk, t) in ((320, 240, 300, 20), (161, 97, 50, 10), (640, 360, 1250, 20), (64, 64, 5000, 0), (40, 33, 7, 35)):
+        frames = np.stack([L.natural_like(w, h, 20 + i) if i % 2 == 0 else rng.integers(0, 256, (h, w)).astype(np.uint8)
+                           for i in range(4)])
+        stale = (rng.integers(0, 256, frames.shape) * (rng.random(frames.shape) < 0.02)).astype(np.uint8)
+        sm, kps, counts = G.fast_batch(dev(frames), nk, t, scoremap=dev(stale))
+        got = G.kps_to_numpy(kps, counts); smh = sm.cpu().numpy()
+        for i in range(4):
+            so = stale[i].copy()
+            want = o_fast(O, frames[i], so, nk, t)
+            assert np.array_equal(smh[i], so), ("scoremap", w, h, i)
+            assert got[i].tobytes() == want.tobytes(), ("fast", w, h, i, len(got[i]), len(want))
+        sm, kps, counts = G.orb_extract_batch(dev(frames), nk, t)
+        got = G.kps_to_numpy(kps, counts)
+        for i in range(4):
+            want = o_orb(O, frames[i], np.zeros_like(frames[i]), nk, t)
+            assert len(got[i]) == len(want), ("orb count", w, h, i)
+            assert got[i].tobytes() == want.tobytes(), ("orb", w, h, i)
+
+
+def test_orb_libdevice_trig_tolerance(G, O):
+    """trig mode 1 (CUDA libdevice): angle within 1e-5 of the reference (north_star tolerance)"""
+    import grayskull_b200 as g
+    a = L.natural_like(320, 240, 5)[None]
+    g.lib().gs_b200_set_trig_mode(1)
+    try:
+        _, kps, counts = G.orb_extract_batch(dev(a), 300, 20)
+    finally:
+        g.lib().gs_b200_set_trig_mode(0)
+    got = G.kps_to_numpy(kps, counts)[0]
+    want = o_orb(O, a[0], np.zeros_like(a[0]), 300, 20)
+    assert len(got) == len(want) > 0
+    assert np.array_equal(got["x"], want["x"]) and np.array_equal(got["y"], want["y"])
+    assert np.abs(got["angle"] - want["angle"]).max() <= 1e-5
+
+
+def test_lbp_vs_oracle(G, O, cas):
+    rng = np.random.default_rng(13)
+    for (w, h) in ((160, 120), (200, 131), (97, 64)):
+        frames = np.stack([L.natural_like(w, h, 40 + i) for i in range(3)])
+        ii = np.stack([o_integral(O, f) for f in frames])
+        iid = dev(ii.view(np.int32))
+        for (mr, sf, mn, mx, st) in ((1000, 1.1, 1.0, 4.0, 2), (5, 1.2, 1.0, 3.0, 1), (1000, 1.25, 1.5, 2.0, 3)):
+            rects, counts = G.lbp_detect_batch(cas, iid, mr, sf, mn, mx, st)
+            got = G.rects_to_numpy(rects, counts)
+            for i in range(3):
+                want = o_detect(O, cas, ii[i], mr, sf, mn, mx, st)
+                assert got[i].tobytes() == want.tobytes(), ("lbp", w, h, mr, sf, i, len(got[i]), len(want))
+
+
+# ---- BASELINE.json sizes: crop checks and size-independent properties ------------------------
+def _crop_check(full_out, frame, fn, r, rng, ncrops=6, size=160):
+    h, w = frame.shape
+    spots = [(0, 0), (w - size, 0), (0, h - size), (w - size, h - size)]
+    spots += [(int(rng.integers(0, w - size)), int(rng.integers(0, h - size))) for _ in range(ncrops)]
+    for (x, y) in spots:
+        xa, ya, xb, yb = max(x - r, 0), max(y - r, 0), min(x + size + r, w), min(y + size + r, h)
+        sub = np.ascontiguousarray(frame[ya:yb, xa:xb])
+        want = fn(sub)
+        # rows/cols whose windows stay inside the crop (or touch the true image border) are exact
+        ix0, iy0 = (0 if xa == 0 else r), (0 if ya == 0 else r)
+        ix1, iy1 = (sub.shape[1] if xb == w else sub.shape[1] - r), (sub.shape[0] if yb == h else sub.shape[0] - r)
+        assert np.array_equal(full_out[ya + iy0:ya + iy1, xa + ix0:xa + ix1], want[iy0:iy1, ix0:ix1]), (x, y)
+
+
+def test_c2_blur_sobel_4096(G, O):
+    """config C2 shape (4096x4096, small batch): crops of the GPU output vs the oracle on the crop"""
+    import torch
+    rng = np.random.default_rng(17)
+    torch.manual_seed(1)
+    src = torch.randint(0, 256, (3, 4096, 4096), dtype=torch.uint8, device="cuda")
+    blur = G.blur_batch(src, 5)
+    sob = G.sobel_batch(blur)
+    f = src[1].cpu().numpy(); b = blur[1].cpu().numpy(); s = sob[1].cpu().numpy()
+    _crop_check(b, f, lambda a: o_blur(O, a, 5), 5, rng)
+    # sobel: compare interior of crops (border rows/cols of a crop are not written by the oracle)
+    for (x, y) in [(0, 0), (4096 - 200, 4096 - 200), (1000, 2000), (3071, 255)]:
+        sub = np.ascontiguousarray(b[y:y + 200, x:x + 200])
+        assert np.array_equal(s[y + 1:y + 199, x + 1:x + 199], o_sobel(O, sub)[1:-1, 1:-1])
+    assert (s[0] == 0).all() and (s[:, 0] == 0).all() and (s[-1] == 0).all() and (s[:, -1] == 0).all()
+    # idempotence-style property: blur of a constant frame is that constant, at full size
+    const = torch.full((1, 4096, 4096), 201, dtype=torch.uint8, device="cuda")
+    assert bool((G.blur_batch(const, 5) == 201).all())
+    # erode <= src <= dilate pointwise, at full size
+    e, d = G.erode_batch(src[:1]), G.dilate_batch(src[:1])
+    assert bool((e <= src[:1]).all()) and bool((d >= src[:1]).all())
+
+
+def test_c3_orb_1080p(G, O):
+    """config C3 shape (1920x1080, nkps=1250, t=20; small batch) against the oracle"""
+    frames = np.stack([L.natural_like(1920, 1080, 60), np.random.default_rng(3).integers(0, 256, (1080, 1920)).astype(np.uint8)])
+    _, kps, counts = G.orb_extract_batch(dev(frames), 1250, 20)
+    got = G.kps_to_numpy(kps, counts)
+    for i in range(2):
+        want = o_orb(O, frames[i], np.zeros_like(frames[i]), 1250, 20)
+        assert len(got[i]) == len(want)
+        assert got[i].tobytes() == want.tobytes(), i
+
+
+def test_c4_integral_lbp_2160p(G, O, cas):
+    """config C4 shape (3840x2160, sf 1.1, scales 1..4, step 2): window count, integral checksum,
+    and full rect-list parity on one frame (the oracle needs a few seconds for it)"""
+    import grayskull_b200 as g
+    assert G.lbp_window_count(cas, 3840, 2160, 1.1, 1.0, 4.0, 2) == 30016520
+    f = L.natural_like(3840, 2160, 77)
+    src = dev(f[None])
+    ii = G.integral_batch(src)
+    iih = ii.cpu().numpy().view(np.uint32)[0]
+    want_ii = o_integral(O, f)
+    assert np.array_equal(iih, want_ii)
+    assert int(iih[-1, -1]) == int(f.astype(np.uint64).sum() % (1 << 32))   # checksum of checksums
+    rects, counts = G.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2)
+    got = G.rects_to_numpy(rects, counts)[0]
+    want = o_detect(O, cas, want_ii, 65536, 1.1, 1.0, 4.0, 2)
+    assert got.tobytes() == want.tobytes(), (len(got), len(want))
