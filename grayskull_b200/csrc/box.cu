@@ -4,7 +4,8 @@
 // count = number of in-image taps = (#in-image columns) * (#in-image rows).  2 B/pixel of
 // compulsory HBM traffic regardless of the radius, so the kernel must stay under ~10 issue
 // slots per pixel.  Fast path (radius 1..7, width % 16 == 0), one 256 x 64 output tile per CTA:
-//   0. one TMA box loads the (256+16) x (64+2r) byte tile; outside the image reads as 0,
+//   0. one TMA box loads the (256+32) x (64+2r) byte tile (16-byte column halo: a TMA box must
+//      start on a 16-byte boundary, see tools/probe/tma_probe.cu); outside the image reads as 0,
 //      which is exactly the contribution of a clipped tap to the SUM;
 //   1. vertical pass: 68 word-columns x 4 row bands; a thread keeps the running column sums of
 //      its 4 columns as two u16x2 words and rolls them down the band with one IADD3 per word
@@ -27,11 +28,12 @@ namespace gsb {
 
 constexpr int BX_TW = 256;                 // output tile width
 constexpr int BX_TH = 64;                  // output tile height
-constexpr int BX_PW = 68;                  // tile pitch in 32-bit words: image bytes [x0-8, x0+264)
-constexpr int BX_SP = 272;                 // column-sum row pitch in u16 (same columns)
+constexpr int BX_PW = 72;                  // tile pitch in 32-bit words: image bytes [x0-16, x0+272)
+constexpr int BX_NC = 68;                  // word-columns that carry column sums: bytes [x0-8, x0+264)
+constexpr int BX_SP = 272;                 // column-sum row pitch in u16 (columns x0-8 .. x0+263)
 constexpr int BX_RMAX = 7;
 constexpr int BX_BANDS = 4, BX_BAND_H = BX_TH / BX_BANDS;   // 16
-constexpr int BX_THREADS = 288;            // 272 phase-1 items (68 x 4) -> 9 warps
+constexpr int BX_THREADS = 288;            // 272 phase-1 items (68 word-columns x 4 bands) -> 9 warps
 constexpr int BX_TILE_WORDS = BX_PW * (BX_TH + 2 * BX_RMAX);
 constexpr int BX_SMEM = BX_TILE_WORDS * 4 + BX_TH * BX_SP * 2 + 226 * 8 + 16;
 
@@ -101,7 +103,7 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, BX_PW * 4 * ROWS);
-    tma_load_3d(tile, &tmap, x0 / 4 - 2, y0 - R, frame, bar);
+    tma_load_3d(tile, &tmap, x0 / 4 - 4, y0 - R, frame, bar);
   }
   if (threadIdx.x >= 1 && threadIdx.x < 226) {   // clipped-count division table
     DivMagic d = div_magic(threadIdx.x);
@@ -110,9 +112,9 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
   mbar_wait(bar, 0);
 
   // ---- phase 1: vertical rolling sums ------------------------------------------------------
-  if (threadIdx.x < BX_PW * BX_BANDS) {
-    const int c = threadIdx.x % BX_PW, band = threadIdx.x / BX_PW;
-    const uint32_t *in = tile + (band * BX_BAND_H) * BX_PW + c;
+  if (threadIdx.x < BX_NC * BX_BANDS) {
+    const int c = threadIdx.x % BX_NC, band = threadIdx.x / BX_NC;
+    const uint32_t *in = tile + (band * BX_BAND_H) * BX_PW + c + 2;   // word of byte x0 - 8 + 4c
     uint32_t se = 0, so = 0;
 #pragma unroll
     for (int i = 0; i < 2 * R; i++) {
@@ -181,7 +183,7 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
     uint2 o;
     if (ADAPTIVE) {
       // dst = src > (int)mean - c ? 255 : 0   (reference :244-245)
-      const uint2 sv = *reinterpret_cast<const uint2 *>(tile + (yo + R) * BX_PW + 2 * lane + 2);
+      const uint2 sv = *reinterpret_cast<const uint2 *>(tile + (yo + R) * BX_PW + 2 * lane + 4);
       uint32_t r0 = 0, r1 = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {

@@ -4,7 +4,9 @@
 // pixels per SM clock, i.e. the whole kernel may spend ~10 issue slots per pixel, so the
 // arithmetic is done on 16-bit lane pairs (two pixels per 32-bit register):
 //   * a TMA box (cp.async.bulk.tensor, zero-filled outside the image) stages a
-//     264 x 130 byte tile (256 x 128 outputs + halo) into shared memory;
+//     288 x 130 byte tile (256 x 128 outputs + a 16-byte halo left and right, 1 row above and
+//     below) into shared memory.  The inner start offset of a TMA box must be a multiple of
+//     16 bytes (measured on B200: tools/probe/tma_probe.cu), hence the 16-byte column halo;
 //   * each warp owns a 16-row band, each lane 8 adjacent columns, and walks down the band
 //     keeping the previous rows' partial results in registers;
 //   * bytes are split into pair words P_k = (pixel x+k, pixel x+k+2) with PRMT/LOP; as fp16
@@ -28,7 +30,7 @@ constexpr int S3_TW = 256;                   // output tile width (pixels)
 constexpr int S3_BH = 16;                    // rows per warp band
 constexpr int S3_WARPS = 8;
 constexpr int S3_TH = S3_BH * S3_WARPS;      // 128 output rows per tile
-constexpr int S3_PW = 68;                    // smem row pitch in words: image bytes [x0-8, x0+264)
+constexpr int S3_PW = 72;                    // smem row pitch in words: image bytes [x0-16, x0+272)
 constexpr int S3_ROWS = S3_TH + 2;           // + 1 halo row above and below
 constexpr unsigned S3_TILE_BYTES = S3_PW * 4 * S3_ROWS;
 
@@ -152,7 +154,7 @@ k_stencil3_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ d
   __syncthreads();
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bar, S3_TILE_BYTES);
-    tma_load_3d(tile, &tmap, x0 / 4 - 2, y0 - 1, frame, &bar);
+    tma_load_3d(tile, &tmap, x0 / 4 - 4, y0 - 1, frame, &bar);
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,7 +172,7 @@ k_stencil3_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ d
     if (x == 0) fix_l = 0xFFFFFFFFu;
     if (x + 8 >= (int)w) fix_r = 0xFFFFFFFFu;
   }
-  const uint32_t *base = tile + (warp * S3_BH) * S3_PW + 2 * lane;  // word of byte x-8
+  const uint32_t *base = tile + (warp * S3_BH) * S3_PW + 2 * lane + 2;  // word of byte x-8
 
   typedef typename RowT<OP>::type Row;
   auto load_row = [&](int r, int yimg) -> Row {
