@@ -94,7 +94,7 @@ def _cpu_worker(args):
     return units, busy
 
 
-def cpu_reference(workload, steps=1, warmup=0, frames_per_core=1, max_cores=None):
+def cpu_reference(workload, steps=1, warmup=0, frames_per_core=1, max_cores=None, budget_s=150.0):
     """Frame-parallel over the host cores (one process per core: gs_orb_extract's static buffer is
     not thread-safe, reference grayskull.h:655).  Returns (value per second, dict)."""
     import _libs as L
@@ -106,11 +106,16 @@ def cpu_reference(workload, steps=1, warmup=0, frames_per_core=1, max_cores=None
         cores = min(cores, max_cores)
     ctx = mp.get_context("fork")
     per_step = []
+    t_begin = time.perf_counter()
     with ctx.Pool(cores) as pool:
         for s in range(warmup + steps):
             res = pool.map(_cpu_worker, [(kind, workload, s * 64 + c, frames_per_core) for c in range(cores)])
             if s >= warmup:   # all cores run concurrently: the step takes as long as the slowest one
                 per_step.append((sum(u for u, _ in res), max(t for _, t in res)))
+            # keep the whole arm within a few minutes: stop early once another step would not fit
+            spent = time.perf_counter() - t_begin
+            if per_step and spent + spent / (s + 1) > budget_s:
+                break
     units = sum(u for u, _ in per_step)
     secs = sum(t for _, t in per_step)
     unit_name = "Mpixels/s" if workload in ("c2", "c3") else "windows/s"
@@ -120,7 +125,7 @@ def cpu_reference(workload, steps=1, warmup=0, frames_per_core=1, max_cores=None
               "c4": "%d frames of 3840x2160 per step, gs_integral + gs_lbp_detect" % (cores * frames_per_core)}[workload]
     return units / secs * scale, {"value": units / secs * scale, "unit": unit_name, "cores": cores, "kind": kind,
                                  "sample": sample + " (gcc -std=c99 -O2, one process per core)",
-                                 "ms_per_step": 1e3 * secs / max(len(per_step), 1)}
+                                 "ms_per_step": 1e3 * secs / max(len(per_step), 1), "steps_run": len(per_step)}
 
 
 # ------------------------------------------------------------------ clocks
@@ -133,7 +138,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -160,14 +165,13 @@ class ClockSampler:
             except ValueError:
                 continue
             mx = max(mx, cmax)
-            if util >= 50:
-                sm.append(clk); pw.append(power)
-                for nme, v in zip(names, parts[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
+            sm.append(clk); pw.append(power)
+            for nme, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
         os.unlink(self.f.name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
-                "power_w": statistics.median(pw) if pw else None, "samples_under_load": len(sm),
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm),
                 "reasons": sorted(reasons)}
 
 
@@ -193,17 +197,20 @@ def gpu_main(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def time_steps(fn, steps, warmup):
+    def time_steps(fn, steps, warmup, sample_clocks=False):
         """W warm-ups, then K steps between barrier+sync, CUDA events on the launching stream"""
         for _ in range(warmup):
             fn()
         barrier()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        if sampler:
+            clock_box.append(sampler.stop())
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -212,6 +219,7 @@ def gpu_main(args):
         return ms
 
     hbm, peak_kind = peaks()
+    clock_box = []
     wl = args.workload
     torch.manual_seed(1234 + rank)
     extra = {}
@@ -274,17 +282,17 @@ def gpu_main(args):
         raise SystemExit("unknown workload " + wl)
 
     # ---- headline: device-resident steps ----
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.gs_b200_launch_count()
-    ms = time_steps(step, args.steps, args.warmup)
+    ms = time_steps(step, args.steps, args.warmup, sample_clocks=True)
     launches = (lib.gs_b200_launch_count() - l0) * args.steps // (args.steps + args.warmup)
-    clocks = sampler.stop() if sampler else None
+    clocks = clock_box[0] if clock_box else None
     value = units_per_step * world * args.steps / (ms * 1e-3) * scale
 
     # ---- per-kernel CUDA-event timing (roofline) ----
     kres = {}
     for name, (fn, algo_bytes) in kernels.items():
-        kms = time_steps(fn, max(args.steps // 2, 5), 3) / max(args.steps // 2, 5)
+        ksteps = max(min(args.steps, 100) // 2, 5)
+        kms = time_steps(fn, ksteps, 3) / ksteps
         kres[name] = {"ms": kms, "algorithmic_bytes": algo_bytes, "achieved_gbs": algo_bytes / (kms * 1e-3) / 1e9,
                       "frac": algo_bytes / (kms * 1e-3) / 1e9 / hbm}
     dom = max(kres, key=lambda k: kres[k]["ms"])
@@ -329,7 +337,7 @@ def gpu_main(args):
             e2e_step()
         barrier()
         t0 = time.perf_counter()
-        ksteps = max(3, args.steps // 10)
+        ksteps = max(3, min(args.steps, 100) // 10)
         for _ in range(ksteps):
             e2e_step()
         barrier()
@@ -346,7 +354,7 @@ def gpu_main(args):
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        _, cpu = cpu_reference(wl, steps=1, warmup=0)
+        _, cpu = cpu_reference(wl, steps=1, warmup=0, max_cores=args.cpu_cores or None)
 
     if rank == 0:
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -365,13 +373,13 @@ def reference_main(args):
     if rank != 0:
         return
     wl = args.workload
-    value, cpu = cpu_reference(wl, steps=max(1, min(args.steps, 5)), warmup=min(args.warmup, 1))
+    value, cpu = cpu_reference(wl, steps=max(1, min(args.steps, 3)), warmup=0, budget_s=150.0)
     unit = cpu["unit"]
     metric = {"c2": "Mpixels/s, gs_blur(r=5) + gs_sobel, 4096x4096 uint8",
               "c3": "Mpixels/s, gs_orb_extract (FAST-9 t=20 + BRIEF-256, nkps=1250), 1920x1080 uint8",
               "c4": "LBP cascade windows/s, gs_integral + gs_lbp_detect frontalface, 3840x2160"}[wl]
     out = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-           "steps": max(1, min(args.steps, 5)), "warmup": min(args.warmup, 1), "ms_per_step": cpu["ms_per_step"],
+           "steps": cpu["steps_run"], "warmup": 0, "ms_per_step": cpu["ms_per_step"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if wl != "c4" else "u32",
            "data": "synthetic", "config": {"workload": cpu["sample"]}, "cpu_baseline": cpu,
            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -381,14 +389,15 @@ def reference_main(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
     ap.add_argument("--e2e-frames", type=int, default=64)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-cores", type=int, default=0, help="cap the cores of the cpu_baseline sample (default: all)")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_main(a)

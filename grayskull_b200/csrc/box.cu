@@ -3,39 +3,42 @@
 // Both need mean = floor(S / count), S = sum of the (2r+1)^2 window clipped to the image,
 // count = number of in-image taps = (#in-image columns) * (#in-image rows).  2 B/pixel of
 // compulsory HBM traffic regardless of the radius, so the kernel must stay under ~10 issue
-// slots per pixel.  Fast path (radius 1..7, width % 16 == 0), one 256 x 64 output tile per CTA:
-//   0. one TMA box loads the (256+32) x (64+2r) byte tile (16-byte column halo: a TMA box must
-//      start on a 16-byte boundary, see tools/probe/tma_probe.cu); outside the image reads as 0,
-//      which is exactly the contribution of a clipped tap to the SUM;
-//   1. vertical pass: 68 word-columns x 4 row bands; a thread keeps the running column sums of
-//      its 4 columns as two u16x2 words and rolls them down the band with one IADD3 per word
-//      (sum += entering row - leaving row on both 16-bit lanes at once: no lane can borrow
-//      because every true lane value is in [0, 65535]); column sums (<= 15*255) go to shared
-//      memory as u16;
-//   2. horizontal pass: a warp per row, a lane per 8 pixels; the (2r+1)-wide window sums for
-//      two adjacent pixels are formed on 16-bit lane pairs from a rolling sum of pair words
-//      (4 integer ops per 2 pixels, radius independent); max (2*7+1)^2*255 = 57375 < 65536;
+// slots per pixel.  Fast path (radius 1..7, width % 16 == 0); no block-level barrier after the
+// tile has landed, every warp is independent:
+//   0. one TMA box loads a 256-column x (BH*warps + 2r)-row byte tile; outside the image reads
+//      as 0, which is exactly the contribution of a clipped tap to the SUM.  Boxes start on
+//      16-byte boundaries (tools/probe/tma_probe.cu), tiles are laid out with a 240-pixel
+//      stride: lanes 0 and 31 of a warp only contribute column sums, lanes 1..30 produce the
+//      240 outputs, so no cross-warp exchange is ever needed;
+//   1. vertical: a lane keeps the running column sums of its 8 columns as four u16x2 words
+//      (adjacent-pixel pairs) and rolls them down its band with one IADD3 per word per row
+//      (sum + entering row - leaving row on both 16-bit lanes at once: no lane can borrow
+//      because every true lane value is in [0, 65535]);
+//   2. horizontal: the neighbours' column sums come by warp shuffle; the (2r+1)-wide window
+//      sums for two adjacent pixels are formed on 16-bit lane pairs from a rolling sum of pair
+//      words (4 integer ops per 2 pixels, radius independent); max (2*7+1)^2*255 = 57375 < 65536;
 //   3. exact division without integer divide: with m = ceil(2^24 / count),
 //        fma_rd(2^23 + S, m * 2^-24, 2^23 - m/2) = 2^23 + floor(S * m / 2^24)
 //      is computed exactly before its single round-down, and floor(S*m/2^24) == S / count for
 //      all S <= 255 * count, count <= 225 (checked exhaustively in tests/test_host_logic.py);
-//      the quotient is the low byte of the float's bit pattern.  Interior pixels use the
-//      compile-time constants for count = (2r+1)^2, clipped pixels a 226-entry table.
+//      the quotient is the low byte of the float's bit pattern.  Tiles whose windows all lie
+//      inside the image use compile-time constants for count = (2r+1)^2 on a branch-free path,
+//      clipped pixels a 226-entry table.
 // Other radii / widths take the generic kernel (one thread per pixel, any radius).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gsb {
 
-constexpr int BX_TW = 256;                 // output tile width
-constexpr int BX_TH = 64;                  // output tile height
-constexpr int BX_PW = 72;                  // tile pitch in 32-bit words: image bytes [x0-16, x0+272)
-constexpr int BX_NC = 68;                  // word-columns that carry column sums: bytes [x0-8, x0+264)
-constexpr int BX_SP = 272;                 // column-sum row pitch in u16 (columns x0-8 .. x0+263)
+constexpr int BX_STRIDE = 240;             // output columns per tile (lanes 1..30 x 8 pixels)
+constexpr int BX_PW = 64;                  // tile pitch in 32-bit words: image bytes [x0-16, x0+240)
 constexpr int BX_RMAX = 7;
-constexpr int BX_BANDS = 4, BX_BAND_H = BX_TH / BX_BANDS;   // 16
-constexpr int BX_THREADS = 288;            // 272 phase-1 items (68 word-columns x 4 bands) -> 9 warps
-constexpr int BX_TILE_WORDS = BX_PW * (BX_TH + 2 * BX_RMAX);
-constexpr int BX_SMEM = BX_TILE_WORDS * 4 + BX_TH * BX_SP * 2 + 226 * 8 + 16;
+constexpr int BX_WARPS = 8;                // warps per CTA, one row band each
+constexpr int BX_BH = 16;                  // rows per band
+constexpr int BX_TH = BX_WARPS * BX_BH;    // 128 output rows per tile
+constexpr int BX_THREADS = BX_WARPS * 32;
+constexpr int BX_TILE_WORDS = BX_PW * (BX_TH + 2 * BX_RMAX);   // 36352 B
 
 struct DivMagic {
   float inv, k;
@@ -77,127 +80,143 @@ __device__ __forceinline__ void window_sums(const uint32_t (&V)[12], uint32_t (&
   }
 }
 
-template <int R, bool ADAPTIVE>
-__global__ void __launch_bounds__(BX_THREADS)
-k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, unsigned w, unsigned h,
-          unsigned tiles_x, unsigned tiles_y, int cparam) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw);
-  uint16_t *colsum = reinterpret_cast<uint16_t *>(smem_raw + BX_TILE_WORDS * 4);
-  float2 *magic = reinterpret_cast<float2 *>(smem_raw + BX_TILE_WORDS * 4 + BX_TH * BX_SP * 2);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + BX_TILE_WORDS * 4 + BX_TH * BX_SP * 2 + 226 * 8);
-
-  unsigned bid = blockIdx.x;
-  const unsigned tx = bid % tiles_x;
-  bid /= tiles_x;
-  const unsigned ty = bid % tiles_y;
-  const unsigned frame = bid / tiles_y;
-  const int x0 = tx * BX_TW, y0 = ty * BX_TH;
-  constexpr int ROWS = BX_TH + 2 * R;
-  constexpr int FULL = (2 * R + 1);
-
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, BX_PW * 4 * ROWS);
-    tma_load_3d(tile, &tmap, x0 / 4 - 4, y0 - R, frame, bar);
-  }
-  if (threadIdx.x >= 1 && threadIdx.x < 226) {   // clipped-count division table
-    DivMagic d = div_magic(threadIdx.x);
-    magic[threadIdx.x] = make_float2(d.inv, d.k);
-  }
-  mbar_wait(bar, 0);
-
-  // ---- phase 1: vertical rolling sums ------------------------------------------------------
-  if (threadIdx.x < BX_NC * BX_BANDS) {
-    const int c = threadIdx.x % BX_NC, band = threadIdx.x / BX_NC;
-    const uint32_t *in = tile + (band * BX_BAND_H) * BX_PW + c + 2;   // word of byte x0 - 8 + 4c
-    uint32_t se = 0, so = 0;
-#pragma unroll
-    for (int i = 0; i < 2 * R; i++) {
-      uint32_t v = in[i * BX_PW];
-      se += v & 0x00FF00FFu;
-      so += prmt(v, 0, 0x4341);
-    }
-    uint16_t *out = colsum + (band * BX_BAND_H) * BX_SP + 4 * c;
-#pragma unroll
-    for (int i = 0; i < BX_BAND_H; i++) {
-      uint32_t vin = in[(i + 2 * R) * BX_PW];
-      se += vin & 0x00FF00FFu;
-      so += prmt(vin, 0, 0x4341);
-      uint2 o;
-      o.x = prmt(se, so, 0x5410);   // (s0, s1)
-      o.y = prmt(se, so, 0x7632);   // (s2, s3)
-      *reinterpret_cast<uint2 *>(out + i * BX_SP) = o;
-      uint32_t vout = in[i * BX_PW];
-      se -= vout & 0x00FF00FFu;
-      so -= prmt(vout, 0, 0x4341);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 2: horizontal window sums, division, store ------------------------------------
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x = x0 + 8 * lane;
-  const bool live = x < (int)w;
-  // lanes whose 8 windows never leave the image horizontally
-  const bool xin = !live || (x - R >= 0 && x + 7 + R <= (int)w - 1);
-  const bool warp_xin = __all_sync(0xFFFFFFFFu, xin);
-  int cw[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) cw[j] = min(x + j + R, (int)w - 1) - max(x + j - R, 0) + 1;
+// division + (threshold +) packing of one row of 8 pixels from its 4 window-sum pair words
+template <int R, bool ADAPTIVE, bool INTERIOR>
+__device__ __forceinline__ uint2 box_finish(const uint32_t (&T)[4], uint2 srcpx, const int (&cw)[8], int ch,
+                                            const float2 *__restrict__ magic, int cparam) {
+  constexpr int FULL = 2 * R + 1;
   constexpr DivMagic FM = {
       (float)((16777216u + FULL * FULL - 1u) / (FULL * FULL)) * 5.9604644775390625e-08f,
       8388608.0f - 0.5f * (float)((16777216u + FULL * FULL - 1u) / (FULL * FULL))};
-  uint8_t *outp = dst + (size_t)frame * w * h + x;
+  uint32_t q[8];
+  if (INTERIOR) {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      q[2 * p] = div_lo(T[p], FM.inv, FM.k);
+      q[2 * p + 1] = div_hi(T[p], FM.inv, FM.k);
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const float2 m0 = magic[cw[2 * p] * ch], m1 = magic[cw[2 * p + 1] * ch];
+      q[2 * p] = div_lo(T[p], m0.x, m0.y);
+      q[2 * p + 1] = div_hi(T[p], m1.x, m1.y);
+    }
+  }
+  uint2 o;
+  if (ADAPTIVE) {
+    // dst = src > (int)mean - c ? 255 : 0   (reference :244-245)
+    uint32_t r0 = 0, r1 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int s0 = (srcpx.x >> (8 * j)) & 0xFF, s1 = (srcpx.y >> (8 * j)) & 0xFF;
+      const int t0 = (int)(q[j] & 0xFF) - cparam, t1 = (int)(q[4 + j] & 0xFF) - cparam;
+      r0 |= (s0 > t0 ? 0xFFu : 0u) << (8 * j);
+      r1 |= (s1 > t1 ? 0xFFu : 0u) << (8 * j);
+    }
+    o.x = r0, o.y = r1;
+  } else {
+    o.x = prmt(prmt(q[0], q[1], 0x0040), prmt(q[2], q[3], 0x0040), 0x5410);
+    o.y = prmt(prmt(q[4], q[5], 0x0040), prmt(q[6], q[7], 0x0040), 0x5410);
+  }
+  return o;
+}
 
-  for (int yo = warp; yo < BX_TH; yo += BX_THREADS / 32) {
-    const int y = y0 + yo;
-    if (y >= (int)h) break;
-    const uint4 *sp = reinterpret_cast<const uint4 *>(colsum + yo * BX_SP + 8 * lane);
+// bytes (b0..b7) of two words -> adjacent-pixel pair words (b0,b1) (b2,b3) (b4,b5) (b6,b7)
+__device__ __forceinline__ void unpack_pairs(uint2 v, uint32_t (&p)[4]) {
+  p[0] = prmt(v.x, 0, 0x4140), p[1] = prmt(v.x, 0, 0x4342);
+  p[2] = prmt(v.y, 0, 0x4140), p[3] = prmt(v.y, 0, 0x4342);
+}
+
+template <int R, bool ADAPTIVE>
+__global__ void __launch_bounds__(BX_THREADS)
+k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, unsigned w, unsigned h, int cparam) {
+  __shared__ __align__(128) uint32_t tile[BX_TILE_WORDS];
+  __shared__ float2 magic[226];
+  __shared__ __align__(8) uint64_t bar;
+  constexpr int ROWS = BX_TH + 2 * R;
+  constexpr int FULL = 2 * R + 1;
+
+  const unsigned frame = blockIdx.z;
+  const int xb = (int)blockIdx.x * BX_STRIDE - 16;   // image column of tile byte 0 (16-B aligned)
+  const int y0 = (int)blockIdx.y * BX_TH;
+  // every window of this tile's outputs lies inside the image: no clipping, no partial rows/cols
+  const bool interior = xb + 8 - R >= 0 && xb + 8 + BX_STRIDE - 1 + R <= (int)w - 1 && y0 - R >= 0 &&
+                        y0 + BX_TH - 1 + R <= (int)h - 1;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (!interior && threadIdx.x >= 1 && threadIdx.x < 226) {   // clipped-count division table
+    const DivMagic d = div_magic(threadIdx.x);
+    magic[threadIdx.x] = make_float2(d.inv, d.k);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, BX_PW * 4 * ROWS);
+    tma_load_3d(tile, &tmap, xb / 4, y0 - R, frame, &bar);
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x = xb + 8 * lane;                 // first of this lane's 8 columns
+  const int yb = y0 + warp * BX_BH;            // first output row of this warp's band
+  const bool out_lane = lane >= 1 && lane <= 30 && x >= 0 && x < (int)w;
+  const uint32_t *in = tile + (warp * BX_BH) * BX_PW + 2 * lane;   // tile row of image row yb - R
+  uint8_t *outp = dst + (size_t)frame * w * h + (size_t)yb * w + x;
+  int cw[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cw[j] = out_lane ? min(x + j + R, (int)w - 1) - max(x + j - R, 0) + 1 : 1;
+
+  mbar_wait(&bar, 0);
+  if (yb >= (int)h) return;                    // warp-uniform
+
+  uint32_t S[4] = {0, 0, 0, 0};                // column sums of the 2R rows above the next window row
+#pragma unroll
+  for (int i = 0; i < 2 * R; i++) {
+    uint32_t e[4];
+    unpack_pairs(*reinterpret_cast<const uint2 *>(in + i * BX_PW), e);
+#pragma unroll
+    for (int k = 0; k < 4; k++) S[k] += e[k];
+  }
+  uint32_t L[4] = {0, 0, 0, 0};                // the row that leaves the window at this step
+
+  auto row_step = [&](int i, auto interior_tag) {
+    constexpr bool INT = decltype(interior_tag)::value;
+    uint32_t e[4];
+    unpack_pairs(*reinterpret_cast<const uint2 *>(in + (i + 2 * R) * BX_PW), e);
+#pragma unroll
+    for (int k = 0; k < 4; k++) S[k] = S[k] + e[k] - L[k];   // one IADD3 per word
+    unpack_pairs(*reinterpret_cast<const uint2 *>(in + i * BX_PW), L);
+    // column sums of columns x-8 .. x+15 as pair words V[0..11]; V[4..7] are this lane's own
     uint32_t V[12], T[4];
-    uint4 a = sp[0], b = sp[1], c4 = sp[2];
-    V[0] = a.x, V[1] = a.y, V[2] = a.z, V[3] = a.w;
-    V[4] = b.x, V[5] = b.y, V[6] = b.z, V[7] = b.w;
-    V[8] = c4.x, V[9] = c4.y, V[10] = c4.z, V[11] = c4.w;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      V[4 + k] = S[k];
+      V[k] = (R == 7 || k > 0) ? __shfl_up_sync(0xFFFFFFFFu, S[k], 1) : 0u;
+      V[8 + k] = (R == 7 || k < 3) ? __shfl_down_sync(0xFFFFFFFFu, S[k], 1) : 0u;
+    }
     window_sums<R>(V, T);
-    const int ch = min(y + R, (int)h - 1) - max(y - R, 0) + 1;
-    uint32_t q[8];
-    if (warp_xin && ch == FULL) {
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        q[2 * p] = div_lo(T[p], FM.inv, FM.k);
-        q[2 * p + 1] = div_hi(T[p], FM.inv, FM.k);
-      }
-    } else {
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        float2 m0 = magic[cw[2 * p] * ch], m1 = magic[cw[2 * p + 1] * ch];
-        q[2 * p] = div_lo(T[p], m0.x, m0.y);
-        q[2 * p + 1] = div_hi(T[p], m1.x, m1.y);
-      }
+    uint2 srcpx = make_uint2(0, 0);
+    if (ADAPTIVE) srcpx = *reinterpret_cast<const uint2 *>(in + (i + R) * BX_PW);
+    int ch = FULL;
+    if (!INT) {
+      const int y = yb + i;
+      ch = min(y + R, (int)h - 1) - max(y - R, 0) + 1;
     }
-    uint2 o;
-    if (ADAPTIVE) {
-      // dst = src > (int)mean - c ? 255 : 0   (reference :244-245)
-      const uint2 sv = *reinterpret_cast<const uint2 *>(tile + (yo + R) * BX_PW + 2 * lane + 4);
-      uint32_t r0 = 0, r1 = 0;
+    const uint2 o = box_finish<R, ADAPTIVE, INT>(T, srcpx, cw, ch, magic, cparam);
+    if (out_lane) st_cs_u2(outp, o);
+    outp += w;
+  };
+
+  if (interior) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        int s0 = (sv.x >> (8 * j)) & 0xFF, s1 = (sv.y >> (8 * j)) & 0xFF;
-        int t0 = (int)(q[j] & 0xFF) - cparam, t1 = (int)(q[4 + j] & 0xFF) - cparam;
-        r0 |= (s0 > t0 ? 0xFFu : 0u) << (8 * j);
-        r1 |= (s1 > t1 ? 0xFFu : 0u) << (8 * j);
-      }
-      o.x = r0, o.y = r1;
-    } else {
-      o.x = prmt(prmt(q[0], q[1], 0x0040), prmt(q[2], q[3], 0x0040), 0x5410);
-      o.y = prmt(prmt(q[4], q[5], 0x0040), prmt(q[6], q[7], 0x0040), 0x5410);
+    for (int i = 0; i < BX_BH; i++) row_step(i, std::true_type{});
+  } else {
+#pragma unroll 1
+    for (int i = 0; i < BX_BH; i++) {
+      if (yb + i >= (int)h) break;             // warp-uniform
+      row_step(i, std::false_type{});
     }
-    if (live) st_cs_u2(outp + (size_t)y * w, o);
   }
 }
 
@@ -227,17 +246,10 @@ __global__ void k_box_generic(uint8_t *__restrict__ dst, const uint8_t *__restri
 template <int R, bool ADAPTIVE>
 static int launch_box_r(const CUtensorMap &tmap, uint8_t *dst, unsigned w, unsigned h, unsigned n,
                         int cparam, cudaStream_t s) {
-  static bool configured = false;  // per instantiation; one device per process
-  if (!configured) {
-    GSB_CHECK(cudaFuncSetAttribute(k_box_tma<R, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   BX_SMEM));
-    configured = true;
-  }
-  const unsigned tiles_x = (w + BX_TW - 1) / BX_TW, tiles_y = (h + BX_TH - 1) / BX_TH;
-  const unsigned long long blocks = (unsigned long long)tiles_x * tiles_y * n;
-  GSB_ASSERT(blocks < 0x7FFFFFFFull);
-  k_box_tma<R, ADAPTIVE><<<(unsigned)blocks, BX_THREADS, BX_SMEM, s>>>(tmap, dst, w, h, tiles_x, tiles_y,
-                                                                        cparam);
+  // tile t covers output columns [240 t - 8, 240 t + 232)
+  const unsigned tiles_x = (w + 8 + BX_STRIDE - 1) / BX_STRIDE, tiles_y = (h + BX_TH - 1) / BX_TH;
+  GSB_ASSERT(tiles_y <= 65535u && n <= 65535u);   // grid y / z limits (launch_box checks n)
+  k_box_tma<R, ADAPTIVE><<<dim3(tiles_x, tiles_y, n), BX_THREADS, 0, s>>>(tmap, dst, w, h, cparam);
   GSB_LAUNCHED(1);
   return 0;
 }
@@ -248,7 +260,7 @@ static int launch_box(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, 
   if (n == 0) return 0;
   CUtensorMap tmap;
   if (r >= 1 && r <= BX_RMAX && tma_ok(src, w) && tma_ok(dst, w) &&
-      make_tmap_u8frames(&tmap, src, w, h, n, BX_PW, BX_TH + 2 * r)) {
+      n <= 65535u && make_tmap_u8frames(&tmap, src, w, h, n, BX_PW, BX_TH + 2 * r)) {
     switch (r) {
       case 1: return launch_box_r<1, ADAPTIVE>(tmap, dst, w, h, n, cparam, s);
       case 2: return launch_box_r<2, ADAPTIVE>(tmap, dst, w, h, n, cparam, s);
