@@ -34,11 +34,27 @@ namespace gsb {
 constexpr int BX_STRIDE = 240;             // output columns per tile (lanes 1..30 x 8 pixels)
 constexpr int BX_PW = 64;                  // tile pitch in 32-bit words: image bytes [x0-16, x0+240)
 constexpr int BX_RMAX = 7;
-constexpr int BX_WARPS = 8;                // warps per CTA, one row band each
-constexpr int BX_BH = 16;                  // rows per band
+#ifndef GSB_BX_WARPS
+#define GSB_BX_WARPS 4
+#endif
+#ifndef GSB_BX_BH
+#define GSB_BX_BH 32
+#endif
+#ifndef GSB_BX_HI_XU
+#define GSB_BX_HI_XU 1                     // 1: high-lane float through the conversion pipe (I2F.U16)
+#endif
+#ifndef GSB_BX_LO_XU
+#define GSB_BX_LO_XU 1                     // 1: low lane too
+#endif
+#ifndef GSB_BX_TOT_IMAD
+#define GSB_BX_TOT_IMAD 1                   // 1: lane totals by IMAD x 0x10001 instead of PRMT + add
+#endif
+constexpr int BX_WARPS = GSB_BX_WARPS;     // warps per CTA, one row band each
+constexpr int BX_BH = GSB_BX_BH;           // rows per band
 constexpr int BX_TH = BX_WARPS * BX_BH;    // 128 output rows per tile
 constexpr int BX_THREADS = BX_WARPS * 32;
-constexpr int BX_TILE_WORDS = BX_PW * (BX_TH + 2 * BX_RMAX);   // 36352 B
+constexpr int BX_TILE_WORDS = BX_PW * (BX_TH + 2 * BX_RMAX);
+constexpr int BX_SMEM = BX_TILE_WORDS * 4 + 226 * 8 + 16;
 
 struct DivMagic {
   float inv, k;
@@ -53,10 +69,36 @@ __host__ __device__ inline DivMagic div_magic(unsigned count) {
 
 // floor(s / count) for a 16-bit s, as the low byte of the returned bit pattern
 __device__ __forceinline__ uint32_t div_lo(uint32_t t, float inv, float k) {
+#if GSB_BX_LO_XU
+  float fl;
+  asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.u16 %0, lo; }" : "=f"(fl) : "r"(t));
+  (void)k;
+  return __float_as_uint(__fmaf_rd(fl, inv, 8388608.0f));
+#else
   return __float_as_uint(__fmaf_rd(__uint_as_float((t & 0xFFFFu) | 0x4B000000u), inv, k));
+#endif
 }
+// high lane: 2^23 + (t >> 16) built with one IMAD.HI (FMA pipe; the ALU pipe is the busy one)
 __device__ __forceinline__ uint32_t div_hi(uint32_t t, float inv, float k) {
-  return __float_as_uint(__fmaf_rd(__uint_as_float(prmt(t, 0x4B000000u, 0x7632)), inv, k));
+#if GSB_BX_HI_XU
+  // float(t >> 16) straight from the high half on the conversion pipe; exact (16-bit integer), and
+  // fma_rd(S, m*2^-24, 2^23) = 2^23 + floor(S*m/2^24) just like the biased form
+  float fh;
+  asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.u16 %0, hi; }" : "=f"(fh) : "r"(t));
+  (void)k;
+  return __float_as_uint(__fmaf_rd(fh, inv, 8388608.0f));
+#else
+  uint32_t f;
+  asm("mad.hi.u32 %0, %1, 65536, 0x4B000000;" : "=r"(f) : "r"(t));
+  return __float_as_uint(__fmaf_rd(__uint_as_float(f), inv, k));
+#endif
+}
+// low bytes of four 2^23+q floats -> one word; the two 8-bit merges are multiply-adds (FMA pipe)
+__device__ __forceinline__ uint32_t pack4(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+  uint32_t a, b;
+  asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(a) : "r"(q1), "r"(q0));   // low 16 bits = q0 | q1 << 8
+  asm("mad.lo.u32 %0, %1, 256, %2;" : "=r"(b) : "r"(q3), "r"(q2));
+  return prmt(a, b, 0x5410);
 }
 
 // window sums for 4 output pixel pairs from 12 pair words V[m] = (s_2m, s_2m+1), s_i = column
@@ -73,9 +115,24 @@ __device__ __forceinline__ void window_sums(const uint32_t (&V)[12], uint32_t (&
 #pragma unroll
   for (int p = 0; p < 4; p++) {
     const int m = M0 + p;
+#if GSB_BX_TOT_IMAD
+    // (ps * 0x10001) >> 16 = lane0 + lane1 (<= 57375, no carry out); * 0x10001 puts it in both lanes
+    uint32_t x16, tot;
+    asm("mad.lo.u32 %0, %1, 0x10001, 0;" : "=r"(x16) : "r"(ps));
+    x16 >>= 16;
+    if (ODD) {
+      const uint32_t edge = prmt(V[m - 1], V[m + NP], 0x5432);
+      asm("mad.lo.u32 %0, %1, 0x10001, %2;" : "=r"(tot) : "r"(x16), "r"(edge));
+      T[p] = tot;
+    } else {
+      asm("mad.lo.u32 %0, %1, 0x10001, 0;" : "=r"(tot) : "r"(x16));
+      T[p] = tot - prmt(V[m + R], V[m], 0x5432);
+    }
+#else
     const uint32_t tot = ps + prmt(ps, ps, 0x1032);   // both lanes = lane0 + lane1
     if (ODD) T[p] = tot + prmt(V[m - 1], V[m + NP], 0x5432);   // + (s_a, s_{a+2R+1})
     else T[p] = tot - prmt(V[m + R], V[m], 0x5432);            // - (s_{a+2R+1}, s_a)
+#endif
     if (p < 3) ps = ps + V[m + NP] - V[m];
   }
 }
@@ -116,8 +173,8 @@ __device__ __forceinline__ uint2 box_finish(const uint32_t (&T)[4], uint2 srcpx,
     }
     o.x = r0, o.y = r1;
   } else {
-    o.x = prmt(prmt(q[0], q[1], 0x0040), prmt(q[2], q[3], 0x0040), 0x5410);
-    o.y = prmt(prmt(q[4], q[5], 0x0040), prmt(q[6], q[7], 0x0040), 0x5410);
+    o.x = pack4(q[0], q[1], q[2], q[3]);
+    o.y = pack4(q[4], q[5], q[6], q[7]);
   }
   return o;
 }
@@ -131,9 +188,10 @@ __device__ __forceinline__ void unpack_pairs(uint2 v, uint32_t (&p)[4]) {
 template <int R, bool ADAPTIVE>
 __global__ void __launch_bounds__(BX_THREADS)
 k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, unsigned w, unsigned h, int cparam) {
-  __shared__ __align__(128) uint32_t tile[BX_TILE_WORDS];
-  __shared__ float2 magic[226];
-  __shared__ __align__(8) uint64_t bar;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw);
+  float2 *magic = reinterpret_cast<float2 *>(smem_raw + BX_TILE_WORDS * 4);
+  uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + BX_TILE_WORDS * 4 + 226 * 8);
   constexpr int ROWS = BX_TH + 2 * R;
   constexpr int FULL = 2 * R + 1;
 
@@ -147,9 +205,11 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
     mbar_init(&bar, 1);
     mbar_fence_init();
   }
-  if (!interior && threadIdx.x >= 1 && threadIdx.x < 226) {   // clipped-count division table
-    const DivMagic d = div_magic(threadIdx.x);
-    magic[threadIdx.x] = make_float2(d.inv, d.k);
+  if (!interior) {                                            // clipped-count division table
+    for (unsigned c = threadIdx.x + 1; c < 226; c += BX_THREADS) {
+      const DivMagic d = div_magic(c);
+      magic[c] = make_float2(d.inv, d.k);
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -249,7 +309,12 @@ static int launch_box_r(const CUtensorMap &tmap, uint8_t *dst, unsigned w, unsig
   // tile t covers output columns [240 t - 8, 240 t + 232)
   const unsigned tiles_x = (w + 8 + BX_STRIDE - 1) / BX_STRIDE, tiles_y = (h + BX_TH - 1) / BX_TH;
   GSB_ASSERT(tiles_y <= 65535u && n <= 65535u);   // grid y / z limits (launch_box checks n)
-  k_box_tma<R, ADAPTIVE><<<dim3(tiles_x, tiles_y, n), BX_THREADS, 0, s>>>(tmap, dst, w, h, cparam);
+  static bool configured = false;                 // per instantiation; one device per process
+  if (!configured) {
+    GSB_CHECK(cudaFuncSetAttribute(k_box_tma<R, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
+    configured = true;
+  }
+  k_box_tma<R, ADAPTIVE><<<dim3(tiles_x, tiles_y, n), BX_THREADS, BX_SMEM, s>>>(tmap, dst, w, h, cparam);
   GSB_LAUNCHED(1);
   return 0;
 }
