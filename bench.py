@@ -142,6 +142,11 @@ class ClockSampler:
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 3.0:     # first sample lands before timing starts
+            if os.path.getsize(self.f.name) > 0:
+                break
+            time.sleep(0.01)
 
     def stop(self):
         if self.p is None:
@@ -278,6 +283,37 @@ def gpu_main(args):
         kernels = {"gs_integral": (lambda: api.integral_batch(src, out=ii), 5.0 * n * h * w),
                    "gs_lbp_detect": (lambda: api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2), 4.0 * n * h * w)}
         launches_per_step = 5
+    elif wl == "ops":
+        # per-op table (every stencil / resampling op of the path at 4096x4096), not a driver line
+        n, h, w = args.batch or 64, H2, W2
+        src = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=dev)
+        out = torch.zeros_like(src)
+        half = torch.empty((n, h // 2, w // 2), dtype=torch.uint8, device=dev)
+        ii = torch.empty((n, h, w), dtype=torch.int32, device=dev)
+        px = float(n * h * w)
+        kernels = {
+            "gs_sobel": (lambda: api.sobel_batch(src, out=out), 2.0 * px),
+            "gs_erode": (lambda: api.erode_batch(src, out=out), 2.0 * px),
+            "gs_dilate": (lambda: api.dilate_batch(src, out=out), 2.0 * px),
+            "gs_blur_r1": (lambda: api.blur_batch(src, 1, out=out), 2.0 * px),
+            "gs_blur_r3": (lambda: api.blur_batch(src, 3, out=out), 2.0 * px),
+            "gs_blur_r5": (lambda: api.blur_batch(src, 5, out=out), 2.0 * px),
+            "gs_blur_r7": (lambda: api.blur_batch(src, 7, out=out), 2.0 * px),
+            "gs_adaptive_threshold_r5": (lambda: api.adaptive_threshold_batch(src, 5, 2, out=out), 2.0 * px),
+            "gs_downsample": (lambda: api.downsample_batch(src, out=half), 1.25 * px),
+            "gs_resize_to_half": (lambda: api.resize_batch(src, w // 2, h // 2, out=half), 1.25 * px),
+            "gs_integral": (lambda: api.integral_batch(src, out=ii), 5.0 * px),
+        }
+
+        def step():
+            for fn, _ in kernels.values():
+                fn()
+
+        units_per_step = n * h * w * len(kernels)
+        unit, scale, metric = "Mpixels/s", 1e-6, "Mpixels/s summed over the per-op table, 4096x4096 uint8"
+        cfg = {"workload": "ops: every stencil/resampling op once, 4096x4096 synthetic uint8, batch %d per GPU" % n,
+               "frames_per_gpu": n, "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (n * h * w / 2**30)}
+        launches_per_step = len(kernels) + 1
     else:
         raise SystemExit("unknown workload " + wl)
 
@@ -299,7 +335,10 @@ def gpu_main(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(wl, {}).get(dom)
+            t = json.load(f).get(wl, {}).get(dom)
+            # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, per frame,
+            # scaled to this launch's frame count (profiles/r01_ncu_c2_summary.txt)
+            traffic = t["dram_bytes_per_frame"] * n if t else None
     except Exception:
         pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kres[dom]["achieved_gbs"], "peak": hbm,
@@ -359,7 +398,7 @@ def gpu_main(args):
     if rank == 0:
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "u8" if wl != "c4" else "u32", "data": "synthetic", "config": cfg, "clocks": clocks,
+               "dtype": "u8" if wl != "c4" else "u32", "data": "synthetic (uniform iid u8, torch.randint; c3/c4: gs_blur r=3 of it)", "config": cfg, "clocks": clocks,
                "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
                "roofline": roofline, "kernels": kres, "cpu_baseline": cpu,
                "tma_path": bool(lib.gs_b200_uses_tma(w, h, src.data_ptr()))}
@@ -391,7 +430,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "ops"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
     ap.add_argument("--e2e-frames", type=int, default=64)
