@@ -193,9 +193,20 @@ def gpu_main(args):
     torch.cuda.set_device(local)
     lib = g.lib()
     g._lib.check(lib.gs_b200_set_device(local), "set_device")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:
+        # NCCL may print a version banner on stdout (NCCL_DEBUG=VERSION): keep stdout for the ONE json line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()            # forces communicator creation now
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
