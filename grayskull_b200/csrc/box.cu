@@ -162,16 +162,22 @@ __device__ __forceinline__ uint2 box_finish(const uint32_t (&T)[4], uint2 srcpx,
   }
   uint2 o;
   if (ADAPTIVE) {
-    // dst = src > (int)mean - c ? 255 : 0   (reference :244-245)
-    uint32_t r0 = 0, r1 = 0;
+    // dst = src > (int)mean - c ? 255 : 0   (reference :244-245), two pixels per 16-bit lane pair:
+    // E = src + (c + 0x7FFF) - mean has bit 15 set exactly when src > mean - c (c clamped to
+    // [-256, 256], beyond which the result saturates anyway); a sign-replicating PRMT turns the
+    // four bit-15s into 0x00 / 0xFF bytes.  q = 0x4B0000mm, so bytes 1 of q are zero.
+    const int cc = max(-256, min(256, cparam));
+    const uint32_t kc = (uint32_t)(cc + 0x7FFF) * 0x10001u;
+    uint32_t e[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int s0 = (srcpx.x >> (8 * j)) & 0xFF, s1 = (srcpx.y >> (8 * j)) & 0xFF;
-      const int t0 = (int)(q[j] & 0xFF) - cparam, t1 = (int)(q[4 + j] & 0xFF) - cparam;
-      r0 |= (s0 > t0 ? 0xFFu : 0u) << (8 * j);
-      r1 |= (s1 > t1 ? 0xFFu : 0u) << (8 * j);
+    for (int p = 0; p < 4; p++) {
+      const uint32_t m = prmt(q[2 * p], q[2 * p + 1], 0x5410);                 // (mean_2p, mean_2p+1)
+      const uint32_t sw = p < 2 ? srcpx.x : srcpx.y;
+      const uint32_t sp = prmt(sw, 0, (p & 1) ? 0x4342 : 0x4140);              // (src_2p, src_2p+1)
+      e[p] = sp + kc - m;
     }
-    o.x = r0, o.y = r1;
+    o.x = prmt(e[0], e[1], 0xFDB9);
+    o.y = prmt(e[2], e[3], 0xFDB9);
   } else {
     o.x = pack4(q[0], q[1], q[2], q[3]);
     o.y = pack4(q[4], q[5], q[6], q[7]);

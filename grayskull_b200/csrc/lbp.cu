@@ -8,11 +8,17 @@
 //             the per-scale truncated feature geometry (int)(int8 * scale) (:799-804) are computed
 //             on the host with the reference's exact fp32 operations and cached on the device,
 //             together with the cascade tables (keyed by content hash);
-//   k_lbp_scan   : one lane per window, 32 x-adjacent windows per warp ("slot").  Each weak reads
-//             the 4x4 corner lattice of its 3x3 cells (16 loads instead of the reference's 36),
-//             stage sums are accumulated with sequential fp32 adds exactly as :808, a lane drops
-//             out at the first failed stage and the warp leaves the cascade when its ballot is
-//             empty.  The surviving-lane ballot of every slot is stored;
+//   k_lbp_scan2  : a CTA owns 2048 consecutive windows of ONE scale (64 "slots" of 32 x-adjacent
+//             windows).  The cascade tables and that scale's feature geometry (precomputed 32-bit
+//             row / column offsets of the 4x4 corner lattice: 16 loads per weak instead of the
+//             reference's 36, one IADD per address) live in shared memory.  Windows run the cascade
+//             in stage groups; after each group the survivors are RE-PACKED into a dense list in
+//             shared memory (warp ballot + one atomic per warp), so later stages run with full
+//             warps instead of a few live lanes (v1 measured 7.8 of 32 lanes active).  Stage sums
+//             are accumulated with sequential fp32 adds exactly as :808.  Hits are recorded as one
+//             bit per window, which keeps the reference's order for free;
+//   k_lbp_scan   : round-1 kernel (lane per window, ballot early exit), kept for cascades whose
+//             tables do not fit shared memory or whose features leave their window;
 //   k_row_scan   : per-frame exclusive scan of the per-CTA hit counts;
 //   k_lbp_emit   : rects written in the reference's (scale, y, x) order, truncated at max_rects
 //             (the reference stops scanning there, :819-823).
@@ -29,8 +35,15 @@ struct ScaleInfo {
   int win_w, win_h, nx, ny;
   unsigned chunks;             // 32-window slots per scan row
   unsigned feat_off;           // first entry of this scale in the feature table
-  unsigned long long slot0;    // first slot of this scale
+  unsigned long long slot0;    // first slot of this scale (a multiple of LBP_SLOTS_PER_CTA)
 };
+struct FeatGeo {               // corner lattice of one feature at one scale, as element offsets
+  int row[4];                  // (fy - 1 + j*fh) * iw
+  int col[4];                  // fx - 1 + i*fw
+};
+constexpr int LBP_SLOTS_PER_CTA = 64;                       // 2048 windows
+constexpr int LBP_WIN_PER_CTA = LBP_SLOTS_PER_CTA * 32;
+constexpr int LBP_MAX_GROUPS = 8;
 struct Weak {
   float left, right;
   uint16_t fidx, sub_off, nsub, pad;
@@ -46,6 +59,9 @@ struct DevCascade {            // pointers into one device blob
   const Weak *weaks;
   const int *subsets;
   const Stage *stages;
+  const FeatGeo *geo;          // [nscales][nfeatures]
+  int group_end[LBP_MAX_GROUPS];   // stage groups: survivors are re-packed after each group
+  int ngroups, nweaks, nsubsets;
   int nscales, nfeatures, nstages;
   unsigned long long total_slots, total_windows;
   int step;
@@ -118,7 +134,7 @@ k_lbp_scan(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCas
     const ScaleInfo sc = dc.scales[si];
     const unsigned long long rel = slot - sc.slot0;
     const unsigned yi = (unsigned)(rel / sc.chunks), xi = (unsigned)(rel % sc.chunks) * 32 + lane;
-    const bool valid = xi < (unsigned)sc.nx;
+    const bool valid = xi < (unsigned)sc.nx && yi < (unsigned)sc.ny;   // padding slots are empty
     const bool hit = cascade_eval<GUARD>(ii, iw, ih, (int)xi * dc.step, (int)yi * dc.step, dc.feat + sc.feat_off,
                                          dc.weaks, dc.subsets, dc.stages, dc.nstages, valid);
     mask = __ballot_sync(0xFFFFFFFFu, hit);
@@ -131,6 +147,159 @@ k_lbp_scan(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCas
 #pragma unroll
     for (int i = 0; i < 8; i++) t += wcnt[i];
     blockcount[(size_t)f * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// one weak classifier for one window (reference gs_lbp_code + gs_lbp_match, :769-788)
+template <bool EDGE>
+__device__ __forceinline__ bool weak_match(const uint32_t *__restrict__ ii, int base, bool x0, bool y0, const FeatGeo &g,
+                                           const Weak &wk, const int *__restrict__ subsets) {
+  uint32_t v[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int rb = base + g.row[j];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int idx = rb + g.col[i];
+      if (EDGE) {   // corner(-1, .) = corner(., -1) = 0: gs_integral_sum's x == 0 / y == 0 guards (:758-760)
+        const bool off = (i == 0 && x0 && g.col[0] < 0) || (j == 0 && y0 && g.row[0] < 0);
+        idx = off ? 0 : idx;
+        const uint32_t t = __ldg(ii + (unsigned)idx);
+        v[j][i] = off ? 0u : t;
+      } else {
+        v[j][i] = __ldg(ii + (unsigned)idx);
+      }
+    }
+  }
+  uint32_t c[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) c[j][i] = v[j + 1][i + 1] + v[j][i] - v[j][i + 1] - v[j + 1][i];
+  const uint32_t m = c[1][1];
+  const int code = ((c[0][0] >= m) << 7) | ((c[0][1] >= m) << 6) | ((c[0][2] >= m) << 5) | ((c[1][2] >= m) << 4) |
+                   ((c[2][2] >= m) << 3) | ((c[2][1] >= m) << 2) | ((c[2][0] >= m) << 1) | ((c[1][0] >= m) << 0);
+  const int idx = code >> 5;
+  return idx < (int)wk.nsub && (((unsigned)subsets[wk.sub_off + idx] >> (code & 31)) & 1u);
+}
+
+__global__ void __launch_bounds__(256)
+k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCascade dc, unsigned *__restrict__ masks,
+            unsigned *__restrict__ blockcount) {
+  extern __shared__ __align__(16) unsigned char lsm[];
+  FeatGeo *s_geo = reinterpret_cast<FeatGeo *>(lsm);
+  Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
+  Stage *s_stage = reinterpret_cast<Stage *>(s_weak + dc.nweaks);
+  int *s_sub = reinterpret_cast<int *>(s_stage + dc.nstages);
+  uint16_t *list_a = reinterpret_cast<uint16_t *>(s_sub + dc.nsubsets);
+  uint16_t *list_b = list_a + LBP_WIN_PER_CTA;
+  __shared__ unsigned hit[LBP_SLOTS_PER_CTA];
+  __shared__ int slot_y[LBP_SLOTS_PER_CTA], slot_x[LBP_SLOTS_PER_CTA];   // window origin of lane 0, -1 = empty slot
+  __shared__ int s_scale;
+  __shared__ unsigned cnt[2];
+
+  const unsigned f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long slot_first = (unsigned long long)blockIdx.x * LBP_SLOTS_PER_CTA;
+  const uint32_t *ii = ii_all + (size_t)f * iw * ih;
+  if (tid == 0) {
+    int si = 0;
+    while (si + 1 < dc.nscales && slot_first >= dc.scales[si + 1].slot0) si++;
+    s_scale = si;
+    cnt[0] = cnt[1] = 0;
+  }
+  __syncthreads();
+  const ScaleInfo sc = dc.scales[s_scale];
+  {  // tables -> shared memory (word copies)
+    const uint32_t *g0 = reinterpret_cast<const uint32_t *>(dc.geo + (size_t)s_scale * dc.nfeatures);
+    uint32_t *d0 = reinterpret_cast<uint32_t *>(s_geo);
+    for (int i = tid; i < dc.nfeatures * 8; i += 256) d0[i] = g0[i];
+    const uint32_t *g1 = reinterpret_cast<const uint32_t *>(dc.weaks);
+    uint32_t *d1 = reinterpret_cast<uint32_t *>(s_weak);
+    for (int i = tid; i < dc.nweaks * 4; i += 256) d1[i] = g1[i];
+    const uint32_t *g2 = reinterpret_cast<const uint32_t *>(dc.stages);
+    uint32_t *d2 = reinterpret_cast<uint32_t *>(s_stage);
+    for (int i = tid; i < dc.nstages * 2; i += 256) d2[i] = g2[i];
+    for (int i = tid; i < dc.nsubsets; i += 256) s_sub[i] = dc.subsets[i];
+  }
+  if (tid < LBP_SLOTS_PER_CTA) {
+    const unsigned long long rel = slot_first + tid - sc.slot0;
+    const bool live = rel < (unsigned long long)sc.chunks * sc.ny;
+    slot_y[tid] = live ? (int)(rel / sc.chunks) * dc.step : -1;
+    slot_x[tid] = live ? (int)(rel % sc.chunks) * 32 : 0;
+    hit[tid] = 0;
+  }
+  __syncthreads();
+
+  // run stages [s0, s1) for window `id` (slot-local id: slot = id >> 5, lane-in-slot = id & 31)
+  auto run = [&](unsigned id, int s0, int s1) -> bool {
+    const int sl = id >> 5, xi = slot_x[sl] + (int)(id & 31);
+    const int y = slot_y[sl], x = xi * dc.step;
+    const int base = y * (int)iw + x;
+    const bool x0 = x == 0, y0 = y == 0;
+    for (int si = s0; si < s1; si++) {
+      const Stage st = s_stage[si];
+      float sum = 0.0f;
+      if (x0 || y0) {
+        for (int i = 0; i < st.n; i++) {
+          const Weak wk = s_weak[st.start + i];
+          sum = __fadd_rn(sum, weak_match<true>(ii, base, x0, y0, s_geo[wk.fidx], wk, s_sub) ? wk.left : wk.right);
+        }
+      } else {
+        for (int i = 0; i < st.n; i++) {
+          const Weak wk = s_weak[st.start + i];
+          sum = __fadd_rn(sum, weak_match<false>(ii, base, false, false, s_geo[wk.fidx], wk, s_sub) ? wk.left : wk.right);
+        }
+      }
+      if (sum < st.thr) return false;
+    }
+    return true;
+  };
+  // survivors -> next list (one shared-memory atomic per warp) or, after the last group, -> hit bits
+  auto keep = [&](bool alive, unsigned id, uint16_t *next, unsigned *next_cnt, bool last) {
+    if (last) {
+      if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));
+      return;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+    unsigned pos = 0;
+    if (lane == 0 && bal) pos = atomicAdd(next_cnt, __popc(bal));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (alive) next[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)id;
+  };
+
+  // group 0: every window of the chunk
+  {
+    const bool last = dc.ngroups == 1;
+    for (unsigned id = tid; id < LBP_WIN_PER_CTA; id += 256) {
+      const int sl = id >> 5;
+      const bool valid = slot_y[sl] >= 0 && slot_x[sl] + (int)(id & 31) < sc.nx;
+      const bool alive = valid && run(id, 0, dc.group_end[0]);
+      keep(alive, id, list_a, &cnt[0], last);
+    }
+  }
+  __syncthreads();
+  uint16_t *cur = list_a, *nxt = list_b;
+  for (int g = 1; g < dc.ngroups; g++) {
+    const unsigned n = cnt[(g - 1) & 1];
+    const bool last = g == dc.ngroups - 1;
+    if (tid == 0) cnt[g & 1] = 0;
+    __syncthreads();
+    for (unsigned i0 = 0; i0 < n; i0 += 256) {     // uniform trip count (ballots inside)
+      const unsigned i = i0 + tid;
+      const unsigned id = i < n ? cur[i] : 0;
+      const bool alive = i < n && run(id, dc.group_end[g - 1], dc.group_end[g]);
+      keep(alive, id, nxt, &cnt[g & 1], last);
+    }
+    __syncthreads();
+    uint16_t *t = cur;
+    cur = nxt, nxt = t;
+  }
+  if (tid < LBP_SLOTS_PER_CTA) masks[(size_t)f * dc.total_slots + slot_first + tid] = hit[tid];
+  if (tid < LBP_SLOTS_PER_CTA / 8) {
+    unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += __popc(hit[tid * 8 + i]);
+    blockcount[(size_t)f * (dc.total_slots / 8) + slot_first / 8 + tid] = t;
   }
 }
 
@@ -235,6 +404,7 @@ static void build_scales(const struct gs_lbp_cascade *c, unsigned iw, unsigned i
     si.feat_off = (unsigned)out.size() * c->nfeatures;
     si.slot0 = slot;
     slot += (unsigned long long)si.chunks * si.ny;
+    slot = (slot + LBP_SLOTS_PER_CTA - 1) / LBP_SLOTS_PER_CTA * LBP_SLOTS_PER_CTA;   // CTAs never straddle scales
     out.push_back(si);
     scale_vals.push_back(s);
     if (out.size() > 4096 || !(scale_factor > 1.0f)) break;  // a non-growing ladder never ends in the reference
@@ -268,6 +438,16 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
       feat[(size_t)s * nf + i] = make_short4((short)fx, (short)fy, (short)fw, (short)fh);
       if (fx < 0 || fy < 0 || fx + 3 * fw > e.scales[s].win_w || fy + 3 * fh > e.scales[s].win_h) safe = false;
     }
+  std::vector<FeatGeo> geo((size_t)ns * nf);
+  for (int s = 0; s < ns; s++)
+    for (int i = 0; i < nf; i++) {
+      const short4 ft = feat[(size_t)s * nf + i];
+      FeatGeo &g = geo[(size_t)s * nf + i];
+      for (int k = 0; k < 4; k++) {
+        g.row[k] = (ft.y - 1 + k * ft.w) * (int)iw;
+        g.col[k] = ft.x - 1 + k * ft.z;
+      }
+    }
   std::vector<Weak> weaks(nw);
   for (int i = 0; i < nw; i++) {
     weaks[i].left = c->weak_left_val[i], weaks[i].right = c->weak_right_val[i];
@@ -282,13 +462,15 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
   auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
   const size_t o_sc = 0, o_ft = align16(o_sc + sizeof(ScaleInfo) * (ns ? ns : 1));
   const size_t o_wk = align16(o_ft + sizeof(short4) * feat.size()), o_sb = align16(o_wk + sizeof(Weak) * nw);
-  const size_t o_st = align16(o_sb + 4 * (size_t)nsub), total = align16(o_st + sizeof(Stage) * nst);
+  const size_t o_st = align16(o_sb + 4 * (size_t)nsub), o_ge = align16(o_st + sizeof(Stage) * nst);
+  const size_t total = align16(o_ge + sizeof(FeatGeo) * geo.size());
   std::vector<unsigned char> host(total, 0);
   if (ns) memcpy(&host[o_sc], e.scales.data(), sizeof(ScaleInfo) * ns);
   if (!feat.empty()) memcpy(&host[o_ft], feat.data(), sizeof(short4) * feat.size());
   memcpy(&host[o_wk], weaks.data(), sizeof(Weak) * nw);
   memcpy(&host[o_sb], c->subsets, 4 * (size_t)nsub);
   memcpy(&host[o_st], stages.data(), sizeof(Stage) * nst);
+  if (!geo.empty()) memcpy(&host[o_ge], geo.data(), sizeof(FeatGeo) * geo.size());
   if (cudaMalloc(&e.blob, total) != cudaSuccess) return nullptr;
   if (cudaMemcpy(e.blob, host.data(), total, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   unsigned char *b = static_cast<unsigned char *>(e.blob);
@@ -297,11 +479,23 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
   e.dc.weaks = reinterpret_cast<const Weak *>(b + o_wk);
   e.dc.subsets = reinterpret_cast<const int *>(b + o_sb);
   e.dc.stages = reinterpret_cast<const Stage *>(b + o_st);
+  e.dc.geo = reinterpret_cast<const FeatGeo *>(b + o_ge);
+  e.dc.nweaks = nw, e.dc.nsubsets = (int)nsub;
+  {  // stage groups: re-pack after each of the first stages (most windows die there), then coarser
+    const int cuts[] = {1, 2, 3, 4, 6, 9, 13};
+    int ng = 0;
+    for (int k = 0; k < 7 && ng < LBP_MAX_GROUPS - 1; k++)
+      if (cuts[k] < nst) e.dc.group_end[ng++] = cuts[k];
+    e.dc.group_end[ng++] = nst;
+    e.dc.ngroups = ng;
+    for (int k = ng; k < LBP_MAX_GROUPS; k++) e.dc.group_end[k] = nst;
+  }
   e.dc.nscales = ns, e.dc.nfeatures = nf, e.dc.nstages = nst, e.dc.step = step;
   e.dc.safe_geometry = safe;
   e.dc.total_slots = 0, e.dc.total_windows = 0;
   for (auto &s : e.scales) {
-    e.dc.total_slots += (unsigned long long)s.chunks * s.ny;
+    const unsigned long long end = s.slot0 + (unsigned long long)s.chunks * s.ny;
+    e.dc.total_slots = (end + LBP_SLOTS_PER_CTA - 1) / LBP_SLOTS_PER_CTA * LBP_SLOTS_PER_CTA;
     e.dc.total_windows += (unsigned long long)s.nx * s.ny;
   }
   if (g_plans.size() >= 16) {  // tiny cache: drop the oldest
@@ -347,8 +541,24 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   unsigned *bcount = static_cast<unsigned *>(gsb::workspace(st, gsb::WS_LBP_B, 4 * (size_t)nblocks * n));
   if (!masks || !bcount) return (int)cudaErrorMemoryAllocation;
   dim3 grid((unsigned)nblocks, n);
-  if (dc.safe_geometry) gsb::k_lbp_scan<false><<<grid, 256, 0, st>>>(ii, iw, ih, dc, masks, bcount);
-  else gsb::k_lbp_scan<true><<<grid, 256, 0, st>>>(ii, iw, ih, dc, masks, bcount);
+  const size_t table_bytes = sizeof(gsb::FeatGeo) * dc.nfeatures + sizeof(gsb::Weak) * dc.nweaks +
+                             sizeof(gsb::Stage) * dc.nstages + 4 * (size_t)dc.nsubsets;
+  const size_t smem2 = table_bytes + 2 * sizeof(uint16_t) * gsb::LBP_WIN_PER_CTA;
+  const bool v2 = dc.safe_geometry && smem2 <= 160 * 1024 && (unsigned long long)iw * ih < 0x7FFFFFFFull &&
+                  getenv("GS_B200_LBP_V1") == nullptr;
+  if (v2) {
+    static size_t configured = 0;
+    if (smem2 > configured) {
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      configured = smem2;
+    }
+    dim3 grid2((unsigned)(dc.total_slots / gsb::LBP_SLOTS_PER_CTA), n);
+    gsb::k_lbp_scan2<<<grid2, 256, smem2, st>>>(ii, iw, ih, dc, masks, bcount);
+  } else if (dc.safe_geometry) {
+    gsb::k_lbp_scan<false><<<grid, 256, 0, st>>>(ii, iw, ih, dc, masks, bcount);
+  } else {
+    gsb::k_lbp_scan<true><<<grid, 256, 0, st>>>(ii, iw, ih, dc, masks, bcount);
+  }
   GSB_LAUNCHED(1);
   gsb::k_row_scan<<<n, 1024, 0, st>>>(bcount, (unsigned)nblocks, counts, max_rects);
   GSB_LAUNCHED(1);
