@@ -176,8 +176,8 @@ __device__ __forceinline__ uint2 box_finish(const uint32_t (&T)[4], uint2 srcpx,
       const uint32_t sp = prmt(sw, 0, (p & 1) ? 0x4342 : 0x4140);              // (src_2p, src_2p+1)
       e[p] = sp + kc - m;
     }
-    o.x = prmt(e[0], e[1], 0xFDB9);
-    o.y = prmt(e[2], e[3], 0xFDB9);
+    o.x = prmt_raw(e[0], e[1], 0xFDB9);
+    o.y = prmt_raw(e[2], e[3], 0xFDB9);
   } else {
     o.x = pack4(q[0], q[1], q[2], q[3]);
     o.y = pack4(q[4], q[5], q[6], q[7]);

@@ -104,6 +104,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return __byte_perm(a, b, sel);
 }
+// raw prmt.b32: selector nibble bit 3 replicates the SIGN of the selected byte over the result byte
+// (__byte_perm masks the selector with 0x7777, so that mode needs inline PTX)
+__device__ __forceinline__ uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 // streaming 64/128-bit stores (outputs are written once and not re-read by the same kernel)
 __device__ __forceinline__ void st_cs_u2(void *p, uint2 v) {
   asm volatile("st.global.cs.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");

@@ -2,13 +2,18 @@
 // ii[y][x] = sum of src over [0..x] x [0..y], modular 32-bit arithmetic (any association order
 // is bit-identical).  Compulsory traffic: 1 B read + 4 B written per pixel.
 //
-// Round-1 implementation: two passes.
+// Batched path (n >= 32, w % 8 == 0, w <= 8192): k_integral_bands, single pass, 5 B/pixel + one
+// re-read of a table row per band (from L2).  A CTA owns a band of 16 rows of one frame, a thread
+// 8 columns.  SAT(x, y) = top(x) + sum_{i<=x} V(i, y), with V the vertical prefix inside the band
+// (thread-local) and top = the table row just above the band.  All band-local work (pixel loads,
+// V, the block-wide horizontal scans of the 16 row totals) happens BEFORE the CTA looks at the band
+// above; then it waits for that band's flag, reads `top`, writes its own LAST row first and raises
+// its flag, so the chain down a frame costs one row round trip per band while the other frames'
+// bands (tickets are handed out band-major across frames) keep the SMs and HBM busy.
+// Fallback (small batches, ragged widths): two passes, 13 B/pixel.
 //   k_integral_rows : a warp per row; each lane takes 4 (vectorised) or 1 pixels per step,
 //                     lane-local prefix + warp shuffle scan + running carry; writes row prefixes.
 //   k_integral_cols : a thread per column; running sum down the rows, in place (coalesced over x).
-// Traffic is 13 B/pixel instead of 5 (the table is written, re-read and re-written); the
-// single-pass chained-band kernel that removes the second trip is the next optimisation
-// ("integral").
 #include "common.cuh"
 
 namespace gsb {
@@ -69,6 +74,120 @@ __global__ void k_integral_cols(uint32_t *__restrict__ ii, unsigned w, unsigned 
   }
 }
 
+constexpr int IB_BH = 16;   // rows per band
+
+// ctrl[0] = ticket counter, ctrl[1 + f * nbands + b] = 1 once band b of frame f has published its last row
+template <int MAXT>   // block-size bound; per-row thread offsets live in shared memory to stay <= 64 registers
+__global__ void __launch_bounds__(MAXT, 1024 / MAXT)
+k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, unsigned w, unsigned h, unsigned n,
+                 unsigned nbands, unsigned *__restrict__ ctrl) {
+  __shared__ uint32_t wtot[IB_BH][32];   // per-row warp totals
+  __shared__ unsigned s_ticket;
+  extern __shared__ uint32_t s_off[];    // [IB_BH][blockDim.x]: exclusive horizontal offset of each thread, per row
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  if (tid == 0) s_ticket = atomicAdd(&ctrl[0], 1u);
+  __syncthreads();
+  const unsigned ticket = s_ticket;
+  const unsigned band = ticket / n, frame = ticket % n;   // band-major: band b of every frame before band b+1
+  const unsigned y0 = band * IB_BH;
+  const unsigned rows = min((unsigned)IB_BH, h - y0);
+  const unsigned x = tid * 8;
+  const bool live = x < w;
+  const uint8_t *sp = src + (size_t)frame * w * h + (size_t)y0 * w + x;
+  uint32_t *dp = ii + (size_t)frame * w * h + (size_t)y0 * w + x;
+
+  // ---- band-local work ----------------------------------------------------------------------
+  // rows beyond the image read as zeros, so acc ends up holding V(., rows-1)
+#define IB_LOAD_ROW(r) ((live && (unsigned)(r) < rows) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)(r) * w)) : make_uint2(0, 0))
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // V(c, r): vertical prefix of this thread's 8 columns
+#pragma unroll
+  for (int r = 0; r < IB_BH; r++) {
+    const uint2 p = IB_LOAD_ROW(r);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      acc[c] += (p.x >> (8 * c)) & 0xFF;
+      acc[4 + c] += (p.y >> (8 * c)) & 0xFF;
+    }
+    uint32_t t = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];
+    uint32_t incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (unsigned)o) incl += u;
+    }
+    if (lane == 31) wtot[r][warp] = incl;
+    s_off[r * blockDim.x + tid] = incl - t;
+  }
+  __syncthreads();
+  for (unsigned r = warp; r < (unsigned)IB_BH; r += nwarps) {   // row r's warp totals -> exclusive warp offsets
+    const uint32_t t = lane < nwarps ? wtot[r][lane] : 0u;
+    uint32_t incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (unsigned)o) incl += u;
+    }
+    wtot[r][lane] = incl - t;
+  }
+  __syncthreads();
+
+  // ---- the row above the band -----------------------------------------------------------------
+  uint32_t top[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (band > 0) {
+    if (tid == 0) {
+      volatile unsigned *flag = ctrl + 1 + (size_t)frame * nbands + (band - 1);
+      while (*flag == 0) __nanosleep(40);
+      __threadfence();
+    }
+    __syncthreads();
+    if (live) {
+      const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(dp - w)), b = __ldcg(reinterpret_cast<const uint4 *>(dp - w) + 1);
+      top[0] = a.x, top[1] = a.y, top[2] = a.z, top[3] = a.w, top[4] = b.x, top[5] = b.y, top[6] = b.z, top[7] = b.w;
+    }
+  }
+  auto emit_row = [&](int r, const uint32_t (&v)[8]) {   // v = V(c, r) for the 8 columns
+    uint32_t o[8];
+    uint32_t run = s_off[r * blockDim.x + tid] + wtot[r][warp];
+#pragma unroll
+    for (int c = 0; c < 8; c++) run += v[c], o[c] = run + top[c];
+    uint4 *q = reinterpret_cast<uint4 *>(dp + (size_t)r * w);
+    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  };
+  // last row first (acc holds V(., rows-1))
+  if (live) {
+    const int last = (int)rows - 1;
+    uint32_t o[8];
+    uint32_t run = s_off[last * blockDim.x + tid] + wtot[last][warp];
+#pragma unroll
+    for (int c = 0; c < 8; c++) run += acc[c], o[c] = run + top[c];
+    uint4 *q = reinterpret_cast<uint4 *>(dp + (size_t)last * w);
+    q[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    q[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    volatile unsigned *flag = ctrl + 1 + (size_t)frame * nbands + band;
+    *flag = 1u;
+  }
+  // remaining rows
+  if (live) {
+    uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < IB_BH - 1; r++) {
+      const uint2 p = IB_LOAD_ROW(r);     // second read of the band's pixels: L1/L2 hits
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        v[c] += (p.x >> (8 * c)) & 0xFF;
+        v[4 + c] += (p.y >> (8 * c)) & 0xFF;
+      }
+      if ((unsigned)r + 1 < rows) emit_row(r, v);
+    }
+  }
+#undef IB_LOAD_ROW
+}
+
 }  // namespace gsb
 
 extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned w, unsigned h, unsigned n,
@@ -76,6 +195,27 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
   GSB_ASSERT(src && ii && w > 0 && h > 0);  // reference :745
   if (n == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(s);
+  const bool aligned = reinterpret_cast<uintptr_t>(src) % 8 == 0 && reinterpret_cast<uintptr_t>(ii) % 16 == 0;
+  if (n >= 32 && w % 8 == 0 && w <= 8192 && aligned && !gsb::force_generic() &&
+      (unsigned long long)n * ((h + gsb::IB_BH - 1) / gsb::IB_BH) < 0x7FFFFFFFull) {
+    const unsigned nbands = (h + gsb::IB_BH - 1) / gsb::IB_BH;
+    const size_t ctrl_bytes = sizeof(unsigned) * (1 + (size_t)n * nbands);
+    unsigned *ctrl = static_cast<unsigned *>(gsb::workspace(st, gsb::WS_INTEGRAL, ctrl_bytes));
+    if (!ctrl) return (int)cudaErrorMemoryAllocation;
+    GSB_CHECK(cudaMemsetAsync(ctrl, 0, ctrl_bytes, st));
+    const unsigned threads = ((w / 8 + 31) / 32) * 32;
+    const size_t smem = sizeof(uint32_t) * gsb::IB_BH * threads;   // <= 64 KB
+    static bool configured = false;
+    if (!configured) {
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_integral_bands<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_integral_bands<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      configured = true;
+    }
+    if (threads <= 512) gsb::k_integral_bands<512><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl);
+    else gsb::k_integral_bands<1024><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl);
+    GSB_LAUNCHED(1);
+    return 0;
+  }
   const unsigned long long rows = (unsigned long long)h * n;
   const unsigned blocks = (unsigned)((rows + 7) / 8);
   const bool vec = (w % 4 == 0) && reinterpret_cast<uintptr_t>(src) % 4 == 0 &&

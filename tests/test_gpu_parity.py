@@ -196,6 +196,17 @@ def test_stencils_vs_oracle(G, O, force_generic):
         g.lib().gs_b200_force_generic(0)
 
 
+def test_integral_single_pass_batches(G, O):
+    """batches of >= 32 frames take the single-pass chained-band kernel (integral.cu): ragged
+    heights, 1..32 warps per row, band counts from 1 to 135"""
+    for (w, h, n) in ((3840, 2160, 34), (256, 37, 33), (4096, 100, 32), (8192, 33, 32), (1920, 1080, 40), (8, 16, 32), (40, 17, 50)):
+        rng = np.random.default_rng(w + h)
+        fr = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+        got = G.integral_batch(dev(fr)).cpu().numpy().view(np.uint32)
+        for i in (0, n // 2, n - 1):
+            assert np.array_equal(got[i], o_integral(O, fr[i])), (w, h, n, i)
+
+
 def test_blur_constant_and_saturated(G, O):
     """all-255 and all-0 frames: the division must be exact at the extremes for every clipped count"""
     for r in range(1, 8):
