@@ -5,7 +5,9 @@
 //                                     darker ring masks; "run of >= 9" is the rotate-AND test; the
 //                                     unsigned-wrap quirk of reference :498 (p < t => every
 //                                     non-brighter sample counts as darker) is reproduced.
-//              pass 2  k_nms_count -> k_row_scan -> k_nms_emit : 3x3 strict-greater NMS over the
+//              (k_fast_score_tiled is the batched form: smem tile, compass pre-test, candidate
+//              compaction; k_fast_score the per-pixel form for foreign-sized score maps)
+//              pass 2  k_nms_mask -> k_row_scan -> k_nms_emit_masks : 3x3 strict-greater NMS over the
 //                                     caller's score map (including the ring cells pass 1 never
 //                                     writes, exactly like reference :517-524) and a SCAN-based
 //                                     compaction, because the reference emits keypoints in raster
@@ -19,6 +21,8 @@
 // The reference calls libm atan2f / sinf (grayskull.h:100-101); trig mode 0 evaluates glibc
 // 2.39's algorithms with IEEE-exact device arithmetic (see dev_sinf / dev_atan2f), so angles and
 // descriptors are bit-identical to the reference on the same box.
+#include <string.h>
+
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -252,6 +256,192 @@ k_nms_emit(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------
+// Tiled FAST score (used when the score map has the image's size): a CTA owns a 128 x 16 pixel
+// tile.  The source tile (+3 halo) is staged in shared memory; every pixel runs the cheap compass
+// pre-test (any 9-arc contains two of the ring positions 0/4/8/12); the few candidates are
+// compacted into a dense list so that the full 16-sample test runs with full warps (in v1 one
+// candidate lane dragged its whole warp through it); scores are assembled in shared memory and
+// written out row-wise.  Arc test on sign bits: funnel-shifting the sign of (hi - v) / (v - lo)
+// into the masks costs one IADD and one SHF per sample and mask.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT_W = 128, FT_H = 16, FT_SW = FT_W + 16, FT_SH = FT_H + 6;   // tile + halo; pitch 144 B = one TMA box row
+
+template <bool TMA>
+__global__ void __launch_bounds__(256)
+k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ src, unsigned w, unsigned h,
+                   uint8_t *__restrict__ score, unsigned t) {
+  __shared__ __align__(128) uint8_t s_src[FT_SH * FT_SW];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint8_t s_score[FT_H * FT_W];
+  __shared__ uint16_t s_list[FT_H * FT_W];
+  __shared__ unsigned s_cnt;
+  const unsigned f = blockIdx.z, tid = threadIdx.x, lane = tid & 31;
+  const int x0 = 3 + blockIdx.x * FT_W, y0 = 3 + blockIdx.y * FT_H;    // first interior pixel of the tile
+  const uint8_t *img = src + (size_t)f * w * h;
+  if (tid == 0) s_cnt = 0;
+  // stage rows y0-3 .. y0+FT_H+2, columns x0-3 .. x0+FT_W+12 (x0 - 3 = 128 * blockIdx.x: 16-B aligned)
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, FT_SH * FT_SW);
+      tma_load_3d(s_src, &tmap, (x0 - 3) / 4, y0 - 3, (int)f, &bar);   // out-of-image reads as 0, never used
+    }
+  } else {
+    for (int i = tid; i < FT_SH * FT_SW; i += 256) {
+      const int r = i / FT_SW, c = i % FT_SW;
+      const int yy = min(y0 - 3 + r, (int)h - 1), xx = min(x0 - 3 + c, (int)w - 1);
+      s_src[i] = __ldg(img + (size_t)yy * w + xx);
+    }
+  }
+  for (int i = tid; i < FT_H * FT_W / 4; i += 256) reinterpret_cast<uint32_t *>(s_score)[i] = 0;
+  if (TMA) mbar_wait(&bar, 0);
+  __syncthreads();
+
+  // phase A: compass pre-test for every pixel of the tile
+  for (int i = tid; i < FT_H * FT_W; i += 256) {      // uniform trip count (ballot inside)
+    const int ly = i / FT_W, lx = i % FT_W;
+    const bool inside = x0 + lx + 3 < (int)w && y0 + ly + 3 < (int)h;
+    const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + 3);
+    const unsigned p = c[0], hi = p + t;
+    const bool wrap = t > p;
+    const unsigned lo = p - t;
+    const unsigned v0 = c[-3 * FT_SW], v4 = c[3], v8 = c[3 * FT_SW], v12 = c[-3];
+    const unsigned nb = (v0 > hi) + (v4 > hi) + (v8 > hi) + (v12 > hi);
+    const unsigned nd = (!(v0 > hi) && (wrap || v0 < lo)) + (!(v4 > hi) && (wrap || v4 < lo)) +
+                        (!(v8 > hi) && (wrap || v8 < lo)) + (!(v12 > hi) && (wrap || v12 < lo));
+    const bool cand = inside && (nb >= 2 || nd >= 2);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cand);
+    unsigned pos = 0;
+    if (lane == 0 && bal) pos = atomicAdd(&s_cnt, __popc(bal));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (cand) s_list[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+  }
+  __syncthreads();
+
+  // phase B: full test on the dense candidate list
+  const unsigned ncand = s_cnt;
+  for (unsigned k = tid; k < ncand; k += 256) {
+    const int i = s_list[k], ly = i / FT_W, lx = i % FT_W;
+    const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + 3);
+    const int p = c[0], hi = p + (int)t, lo = p - (int)t;
+    unsigned bright = 0, dark = 0;
+    int mind = 255;
+#define FAST_TAP2(i_, dx, dy)                                                       \
+  {                                                                                 \
+    const int v = c[(dy) * FT_SW + (dx)];                                           \
+    bright = __funnelshift_l((unsigned)(hi - v), bright, 1);   /* bit = (v > hi) */  \
+    dark = __funnelshift_l((unsigned)(v - lo), dark, 1);       /* bit = (v < lo) */  \
+    mind = min(mind, abs(v - p));                                                   \
+  }
+    FAST_RING(FAST_TAP2)
+#undef FAST_TAP2
+    bright &= 0xFFFFu;
+    // reference :498: when t > p the unsigned p - t wraps and every non-brighter sample is "darker"
+    dark = (t > (unsigned)p) ? (~bright & 0xFFFFu) : (dark & 0xFFFFu);
+    // the masks are bit-reversed w.r.t. the ring index (sample 0 ends up in bit 15): circular
+    // runs are invariant under reversal
+    if (run9(bright) || run9(dark)) s_score[i] = (uint8_t)mind;
+  }
+  __syncthreads();
+
+  // phase C: write the tile's scores (interior pixels only)
+  for (int i = tid; i < FT_H * FT_W; i += 256) {
+    const int ly = i / FT_W, lx = i % FT_W;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x + 3 < (int)w && y + 3 < (int)h) score[(size_t)f * w * h + (size_t)y * w + x] = s_score[i];
+  }
+}
+
+// NMS in one pass: per interior row a bit mask of survivors (pixel x -> bit x & 31 of word x >> 5)
+// and their count.  A thread owns 4 pixels (one aligned word of the score row); all-zero words --
+// the common case -- skip the neighbour rows entirely.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_nms_mask(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h, unsigned mw,
+           unsigned *__restrict__ masks, unsigned *__restrict__ rowcount) {
+  __shared__ unsigned wsum[8];
+  const unsigned rows = h - 6, y = 3 + blockIdx.x, f = blockIdx.y;
+  const uint8_t *sm = score + (size_t)f * sw * sh;
+  unsigned *mrow = masks + ((size_t)f * rows + blockIdx.x) * mw;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned total = 0;
+  for (unsigned xb = 0; xb < w; xb += 1024) {        // 256 threads x 4 pixels
+    const unsigned x4 = xb + threadIdx.x * 4;
+    unsigned nib = 0;
+    if (x4 < w) {
+      bool any = true;
+      if (VEC) any = __ldg(reinterpret_cast<const uint32_t *>(sm + (size_t)y * sw + x4)) != 0;
+      if (any) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const unsigned x = x4 + j;
+          unsigned s;
+          if (x >= 3 && x + 3 < w && nms_keep(sm, sw, sh, x, y, s)) nib |= 1u << j;
+        }
+      }
+    }
+    // 8 lanes x 4 bits -> one 32-pixel mask word
+    unsigned m = nib << (4 * (lane & 7));
+    m |= __shfl_xor_sync(0xFFFFFFFFu, m, 1);
+    m |= __shfl_xor_sync(0xFFFFFFFFu, m, 2);
+    m |= __shfl_xor_sync(0xFFFFFFFFu, m, 4);
+    const unsigned word = (x4 >> 5);
+    if ((lane & 7) == 0 && word < mw) mrow[word] = m;
+    total += __popc(nib);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+  if (lane == 0) wsum[warp] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) t += wsum[i];
+    rowcount[(size_t)f * rows + blockIdx.x] = t;
+  }
+}
+
+// emit from the masks: one warp per interior row; rows past the cap or without survivors exit
+__global__ void __launch_bounds__(256)
+k_nms_emit_masks(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h, unsigned mw,
+                 const unsigned *__restrict__ masks, const unsigned *__restrict__ rowoff, unsigned rows_total,
+                 KpRec *__restrict__ kps, unsigned nkps) {
+  const unsigned rows = h - 6;
+  const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31;
+  if (gw >= rows_total) return;
+  const unsigned f = (unsigned)(gw / rows), row = (unsigned)(gw % rows), y = 3 + row;
+  unsigned base = rowoff[gw];
+  if (base >= nkps) return;
+  const unsigned *mrow = masks + gw * mw;
+  const uint8_t *sm = score + (size_t)f * sw * sh;
+  for (unsigned w0 = 0; w0 < mw && base < nkps; w0 += 32) {
+    const unsigned m = (w0 + lane < mw) ? mrow[w0 + lane] : 0u;
+    unsigned c = __popc(m), incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (unsigned)o) incl += u;
+    }
+    unsigned pos = base + incl - c;
+    unsigned bits = m;
+    while (bits && pos < nkps) {
+      const unsigned b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const unsigned x = (w0 + lane) * 32 + b;
+      uint4 *o = reinterpret_cast<uint4 *>(kps + (size_t)f * nkps + pos);
+      o[0] = make_uint4(x, y, sm_get(sm, sw, sh, x, y), 0), o[1] = make_uint4(0, 0, 0, 0), o[2] = make_uint4(0, 0, 0, 0);
+      pos++;
+    }
+    base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // ORB: stable sort by response, margin filter, cap
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned ORB_MAXC = 5000;  // the reference's static candidates[5000] (grayskull.h:655)
@@ -425,20 +615,37 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
     GSB_CHECK(cudaMemsetAsync(counts, 0, sizeof(unsigned) * n, s));
     return 0;
   }
-  const unsigned rows = h - 6;
+  const unsigned rows = h - 6, mw = (w + 31) / 32;
   unsigned *rowcount = static_cast<unsigned *>(workspace(s, WS_FAST_A, sizeof(unsigned) * (size_t)rows * n));
-  if (!rowcount) return (int)cudaErrorMemoryAllocation;
-  {
-    dim3 block(32, 8), grid((w - 6 + 31) / 32, (h - 6 + 7) / 8, n < 65535u ? n : 65535u);
-    k_fast_score<<<grid, block, 0, s>>>(src, w, h, n, score, sw, sh, threshold);
-    GSB_LAUNCHED(1);
-  }
+  unsigned *masks = static_cast<unsigned *>(workspace(s, WS_FAST_B, sizeof(unsigned) * (size_t)rows * n * mw));
+  if (!rowcount || !masks) return (int)cudaErrorMemoryAllocation;
   GSB_ASSERT(n <= 65535u && rows <= 0x7FFFFFFFu);
-  k_nms_count<<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, rowcount);
+  if (sw == w && sh == h && !force_generic()) {
+    dim3 grid((w - 6 + FT_W - 1) / FT_W, (h - 6 + FT_H - 1) / FT_H, n);
+    GSB_ASSERT(grid.y <= 65535u);
+    CUtensorMap tmap;
+    if (tma_ok(src, w) && make_tmap_u8frames(&tmap, src, w, h, n, FT_SW / 4, FT_SH))
+      k_fast_score_tiled<true><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
+    else {
+      memset(&tmap, 0, sizeof(tmap));
+      k_fast_score_tiled<false><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
+    }
+  } else {   // foreign-sized score map (single-image gs_fast only): gs_set semantics per pixel
+    dim3 block(32, 8), grid((w - 6 + 31) / 32, (h - 6 + 7) / 8, n);
+    k_fast_score<<<grid, block, 0, s>>>(src, w, h, n, score, sw, sh, threshold);
+  }
+  GSB_LAUNCHED(1);
+  if (sw % 4 == 0 && reinterpret_cast<uintptr_t>(score) % 4 == 0 && sw >= w)
+    k_nms_mask<true><<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
+  else
+    k_nms_mask<false><<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
   GSB_LAUNCHED(1);
   k_row_scan<<<n, 1024, 0, s>>>(rowcount, rows, counts, nkps);
   GSB_LAUNCHED(1);
-  k_nms_emit<<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, rowcount, kps, nkps);
+  const unsigned long long rows_total = (unsigned long long)rows * n;
+  GSB_ASSERT(rows_total < 0x7FFFFFFFull);
+  k_nms_emit_masks<<<(unsigned)((rows_total + 7) / 8), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount,
+                                                                    (unsigned)rows_total, kps, nkps);
   GSB_LAUNCHED(1);
   return 0;
 }
