@@ -41,8 +41,15 @@ struct FeatGeo {               // corner lattice of one feature at one scale, as
   int row[4];                  // (fy - 1 + j*fh) * iw
   int col[4];                  // fx - 1 + i*fw
 };
-constexpr int LBP_SLOTS_PER_CTA = 64;                       // 2048 windows
+#ifndef GSB_LBP_SLOTS
+#define GSB_LBP_SLOTS 128
+#endif
+#ifndef GSB_LBP_THREADS
+#define GSB_LBP_THREADS 256
+#endif
+constexpr int LBP_SLOTS_PER_CTA = GSB_LBP_SLOTS;            // 32 windows each
 constexpr int LBP_WIN_PER_CTA = LBP_SLOTS_PER_CTA * 32;
+constexpr int LBP_THREADS = GSB_LBP_THREADS;
 constexpr int LBP_MAX_GROUPS = 8;
 struct Weak {
   float left, right;
@@ -183,7 +190,7 @@ __device__ __forceinline__ bool weak_match(const uint32_t *__restrict__ ii, int 
   return idx < (int)wk.nsub && (((unsigned)subsets[wk.sub_off + idx] >> (code & 31)) & 1u);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LBP_THREADS)
 k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCascade dc, unsigned *__restrict__ masks,
             unsigned *__restrict__ blockcount) {
   extern __shared__ __align__(16) unsigned char lsm[];
@@ -212,21 +219,21 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
   {  // tables -> shared memory (word copies)
     const uint32_t *g0 = reinterpret_cast<const uint32_t *>(dc.geo + (size_t)s_scale * dc.nfeatures);
     uint32_t *d0 = reinterpret_cast<uint32_t *>(s_geo);
-    for (int i = tid; i < dc.nfeatures * 8; i += 256) d0[i] = g0[i];
+    for (int i = tid; i < dc.nfeatures * 8; i += LBP_THREADS) d0[i] = g0[i];
     const uint32_t *g1 = reinterpret_cast<const uint32_t *>(dc.weaks);
     uint32_t *d1 = reinterpret_cast<uint32_t *>(s_weak);
-    for (int i = tid; i < dc.nweaks * 4; i += 256) d1[i] = g1[i];
+    for (int i = tid; i < dc.nweaks * 4; i += LBP_THREADS) d1[i] = g1[i];
     const uint32_t *g2 = reinterpret_cast<const uint32_t *>(dc.stages);
     uint32_t *d2 = reinterpret_cast<uint32_t *>(s_stage);
-    for (int i = tid; i < dc.nstages * 2; i += 256) d2[i] = g2[i];
-    for (int i = tid; i < dc.nsubsets; i += 256) s_sub[i] = dc.subsets[i];
+    for (int i = tid; i < dc.nstages * 2; i += LBP_THREADS) d2[i] = g2[i];
+    for (int i = tid; i < dc.nsubsets; i += LBP_THREADS) s_sub[i] = dc.subsets[i];
   }
-  if (tid < LBP_SLOTS_PER_CTA) {
-    const unsigned long long rel = slot_first + tid - sc.slot0;
+  for (unsigned sl = tid; sl < LBP_SLOTS_PER_CTA; sl += LBP_THREADS) {
+    const unsigned long long rel = slot_first + sl - sc.slot0;
     const bool live = rel < (unsigned long long)sc.chunks * sc.ny;
-    slot_y[tid] = live ? (int)(rel / sc.chunks) * dc.step : -1;
-    slot_x[tid] = live ? (int)(rel % sc.chunks) * 32 : 0;
-    hit[tid] = 0;
+    slot_y[sl] = live ? (int)(rel / sc.chunks) * dc.step : -1;
+    slot_x[sl] = live ? (int)(rel % sc.chunks) * 32 : 0;
+    hit[sl] = 0;
   }
   __syncthreads();
 
@@ -270,7 +277,7 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
   // group 0: every window of the chunk
   {
     const bool last = dc.ngroups == 1;
-    for (unsigned id = tid; id < LBP_WIN_PER_CTA; id += 256) {
+    for (unsigned id = tid; id < LBP_WIN_PER_CTA; id += LBP_THREADS) {
       const int sl = id >> 5;
       const bool valid = slot_y[sl] >= 0 && slot_x[sl] + (int)(id & 31) < sc.nx;
       const bool alive = valid && run(id, 0, dc.group_end[0]);
@@ -284,7 +291,7 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
     const bool last = g == dc.ngroups - 1;
     if (tid == 0) cnt[g & 1] = 0;
     __syncthreads();
-    for (unsigned i0 = 0; i0 < n; i0 += 256) {     // uniform trip count (ballots inside)
+    for (unsigned i0 = 0; i0 < n; i0 += LBP_THREADS) {     // uniform trip count (ballots inside)
       const unsigned i = i0 + tid;
       const unsigned id = i < n ? cur[i] : 0;
       const bool alive = i < n && run(id, dc.group_end[g - 1], dc.group_end[g]);
@@ -294,12 +301,12 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
     uint16_t *t = cur;
     cur = nxt, nxt = t;
   }
-  if (tid < LBP_SLOTS_PER_CTA) masks[(size_t)f * dc.total_slots + slot_first + tid] = hit[tid];
-  if (tid < LBP_SLOTS_PER_CTA / 8) {
+  for (unsigned sl = tid; sl < LBP_SLOTS_PER_CTA; sl += LBP_THREADS) masks[(size_t)f * dc.total_slots + slot_first + sl] = hit[sl];
+  for (unsigned g8 = tid; g8 < LBP_SLOTS_PER_CTA / 8; g8 += LBP_THREADS) {
     unsigned t = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) t += __popc(hit[tid * 8 + i]);
-    blockcount[(size_t)f * (dc.total_slots / 8) + slot_first / 8 + tid] = t;
+    for (int i = 0; i < 8; i++) t += __popc(hit[g8 * 8 + i]);
+    blockcount[(size_t)f * (dc.total_slots / 8) + slot_first / 8 + g8] = t;
   }
 }
 
@@ -553,7 +560,7 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
       configured = smem2;
     }
     dim3 grid2((unsigned)(dc.total_slots / gsb::LBP_SLOTS_PER_CTA), n);
-    gsb::k_lbp_scan2<<<grid2, 256, smem2, st>>>(ii, iw, ih, dc, masks, bcount);
+    gsb::k_lbp_scan2<<<grid2, gsb::LBP_THREADS, smem2, st>>>(ii, iw, ih, dc, masks, bcount);
   } else if (dc.safe_geometry) {
     gsb::k_lbp_scan<false><<<grid, 256, 0, st>>>(ii, iw, ih, dc, masks, bcount);
   } else {
