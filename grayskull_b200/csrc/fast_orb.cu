@@ -301,24 +301,49 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
   if (TMA) mbar_wait(&bar, 0);
   __syncthreads();
 
-  // phase A: compass pre-test for every pixel of the tile
-  for (int i = tid; i < FT_H * FT_W; i += 256) {      // uniform trip count (ballot inside)
-    const int ly = i / FT_W, lx = i % FT_W;
-    const bool inside = x0 + lx + 3 < (int)w && y0 + ly + 3 < (int)h;
-    const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + 3);
-    const unsigned p = c[0], hi = p + t;
-    const bool wrap = t > p;
-    const unsigned lo = p - t;
-    const unsigned v0 = c[-3 * FT_SW], v4 = c[3], v8 = c[3 * FT_SW], v12 = c[-3];
-    const unsigned nb = (v0 > hi) + (v4 > hi) + (v8 > hi) + (v12 > hi);
-    const unsigned nd = (!(v0 > hi) && (wrap || v0 < lo)) + (!(v4 > hi) && (wrap || v4 < lo)) +
-                        (!(v8 > hi) && (wrap || v8 < lo)) + (!(v12 > hi) && (wrap || v12 < lo));
-    const bool cand = inside && (nb >= 2 || nd >= 2);
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cand);
-    unsigned pos = 0;
-    if (lane == 0 && bal) pos = atomicAdd(&s_cnt, __popc(bal));
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    if (cand) s_list[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+  // phase A: compass pre-test for every pixel of the tile.  Thread = column lx, rows ly0, ly0+2, ...
+  // "at least two of the four compass samples are brighter (darker)" is evaluated on the SIGN bits
+  // of hi - v (v - lo): two-or-more-of-four = (a&b) | (c&d) | ((a|b) & (c|d)).
+  {
+    const int lx = tid & (FT_W - 1);
+    const bool col_in = x0 + lx + 3 < (int)w;
+    const int ti = (int)t;
+    unsigned flags = 0;                              // bit k: row (tid >> 7) + 2k of this column is a candidate
+#pragma unroll
+    for (int k = 0; k < FT_H / 2; k++) {
+      const int ly = (tid >> 7) + 2 * k;
+      const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + 3);
+      const int p = c[0], hi = p + ti, lo = p - ti;
+      const int v0 = c[-3 * FT_SW], v4 = c[3], v8 = c[3 * FT_SW], v12 = c[-3];
+      const int b0 = hi - v0, b1 = hi - v4, b2 = hi - v8, b3 = hi - v12;      // negative <=> brighter
+      const int d0 = v0 - lo, d1 = v4 - lo, d2 = v8 - lo, d3 = v12 - lo;      // negative <=> darker (no wrap)
+      const int two_b = (b0 & b1) | (b2 & b3) | ((b0 | b1) & (b2 | b3));
+      const int two_d = (d0 & d1) | (d2 & d3) | ((d0 | d1) & (d2 | d3));
+      // wrap (t > p, reference :498): darker = not brighter; two or more darker <=> not (three or more brighter)
+      const int three_b = (b0 & b1 & (b2 | b3)) | (b2 & b3 & (b0 | b1));
+      const int dsel = lo < 0 ? ~three_b : two_d;
+      const bool cand = col_in && y0 + ly + 3 < (int)h && ((two_b | dsel) < 0);
+      flags |= (unsigned)cand << k;
+    }
+    // one compaction per thread: warp-exclusive scan of the per-thread candidate counts, one
+    // shared-memory atomic per warp (candidates are rare: the common case is an all-zero ballot)
+    if (__any_sync(0xFFFFFFFFu, flags != 0)) {
+      const unsigned c = __popc(flags);
+      unsigned incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += u;
+      }
+      unsigned base = 0;
+      if (lane == 31) base = atomicAdd(&s_cnt, incl);
+      base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
+      while (flags) {
+        const int k = __ffs(flags) - 1;
+        flags &= flags - 1;
+        s_list[base++] = (uint16_t)(((tid >> 7) + 2 * k) * FT_W + lx);
+      }
+    }
   }
   __syncthreads();
 
@@ -517,6 +542,35 @@ k_orb_select(const KpRec *__restrict__ cand, const unsigned *__restrict__ cand_c
   if (tid == 0) counts[f] = min(running, nkps);
 }
 
+// r = 15 (the only radius gs_orb_extract uses, reference :658): row dy of the disc spans |dx| <= hw(dy),
+// hw = floor(sqrt(225 - dy^2)), known at compile time; lane = dx + 15.
+__device__ __forceinline__ constexpr int disc15_hw(int dy) {
+  int a = dy < 0 ? -dy : dy, hw = 0;
+  while ((hw + 1) * (hw + 1) + a * a <= 225) hw++;
+  return hw;
+}
+__device__ __forceinline__ void disc_moments15(const uint8_t *img, unsigned w, int x, int y, unsigned lane, int &m01,
+                                               int &m10) {
+  const int dx = (int)lane - 15;
+  const int adx = dx < 0 ? -dx : dx;
+  const uint8_t *p = img + (size_t)(y - 15) * w + (x + dx);   // lane 31 is never dereferenced
+  int a01 = 0, rowsum = 0, a10 = 0;
+#pragma unroll
+  for (int dy = -15; dy <= 15; dy++) {
+    const int v = (adx <= disc15_hw(dy)) ? (int)__ldg(p) : 0;
+    a01 += dy * v;
+    rowsum += v;
+    p += w;
+  }
+  a10 = dx * rowsum;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a01 += __shfl_xor_sync(0xFFFFFFFFu, a01, o);
+    a10 += __shfl_xor_sync(0xFFFFFFFFu, a10, o);
+  }
+  m01 = a01, m10 = a10;
+}
+
 // intensity-centroid moments over the disc dx^2 + dy^2 <= r^2; lanes = dx (r <= 15 per pass)
 __device__ __forceinline__ void disc_moments(const uint8_t *img, unsigned w, int x, int y, int r, unsigned lane,
                                              int &m01, int &m10) {
@@ -579,7 +633,7 @@ k_orb_describe(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *_
   const uint8_t *img = src + (size_t)f * w * h;
   const int x = (int)k->w[0], y = (int)k->w[1];
   int m01, m10;
-  disc_moments(img, w, x, y, 15, lane, m01, m10);
+  disc_moments15(img, w, x, y, lane, m01, m10);
   const float angle = orient_from_moments(m01, m10, trig_mode);
   uint32_t desc[8];
   brief_words(img, w, h, x, y, angle, lane, trig_mode, desc);

@@ -52,25 +52,53 @@ __device__ __forceinline__ void resize_axis(unsigned i, unsigned sdim, unsigned 
   frac = __fsub_rn(s, (float)i0);
 }
 
-__global__ void k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src,
-                         unsigned sw, unsigned sh, unsigned n) {
-  const unsigned x = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= dw || y >= dh) return;
-  unsigned x0, x1, y0, y1;
-  float dx, dy;
-  resize_axis(x, sw, dw, x0, x1, dx);
-  resize_axis(y, sh, dh, y0, y1, dy);
-  const float omx = __fsub_rn(1.0f, dx), omy = __fsub_rn(1.0f, dy);
+// A thread produces 4 adjacent dst pixels for RS_ROWS rows: the x-axis coefficients (two IEEE
+// divisions per pixel in the reference's formula) are computed once per thread, the y-axis ones once
+// per row, and the 4 results leave as one 32-bit store.
+constexpr int RS_ROWS = 8;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src, unsigned sw,
+         unsigned sh, unsigned n) {
+  const unsigned x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
+  const unsigned yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * RS_ROWS;
+  if (x >= dw || yb >= dh) return;
+  unsigned x0[4], x1[4];
+  float dx[4], omx[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    resize_axis(min(x + j, dw - 1), sw, dw, x0[j], x1[j], dx[j]);
+    omx[j] = __fsub_rn(1.0f, dx[j]);
+  }
   for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
     const uint8_t *s = src + (size_t)f * sw * sh;
-    const float c00 = (float)__ldg(s + (size_t)y0 * sw + x0), c01 = (float)__ldg(s + (size_t)y0 * sw + x1);
-    const float c10 = (float)__ldg(s + (size_t)y1 * sw + x0), c11 = (float)__ldg(s + (size_t)y1 * sw + x1);
-    float p = __fmul_rn(__fmul_rn(c00, omx), omy);
-    p = __fadd_rn(p, __fmul_rn(__fmul_rn(c01, dx), omy));
-    p = __fadd_rn(p, __fmul_rn(__fmul_rn(c10, omx), dy));
-    p = __fadd_rn(p, __fmul_rn(__fmul_rn(c11, dx), dy));
-    dst[(size_t)f * dw * dh + (size_t)y * dw + x] = (uint8_t)__float2uint_rz(p);
+    uint8_t *d = dst + (size_t)f * dw * dh;
+    for (unsigned r = 0; r < (unsigned)RS_ROWS && yb + r < dh; r++) {
+      const unsigned y = yb + r;
+      unsigned y0, y1;
+      float dy;
+      resize_axis(y, sh, dh, y0, y1, dy);
+      const float omy = __fsub_rn(1.0f, dy);
+      const uint8_t *r0 = s + (size_t)y0 * sw, *r1 = s + (size_t)y1 * sw;
+      uint32_t out = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float c00 = (float)__ldg(r0 + x0[j]), c01 = (float)__ldg(r0 + x1[j]);
+        const float c10 = (float)__ldg(r1 + x0[j]), c11 = (float)__ldg(r1 + x1[j]);
+        float p = __fmul_rn(__fmul_rn(c00, omx[j]), omy);
+        p = __fadd_rn(p, __fmul_rn(__fmul_rn(c01, dx[j]), omy));
+        p = __fadd_rn(p, __fmul_rn(__fmul_rn(c10, omx[j]), dy));
+        p = __fadd_rn(p, __fmul_rn(__fmul_rn(c11, dx[j]), dy));
+        out |= (__float2uint_rz(p) & 0xFFu) << (8 * j);
+      }
+      uint8_t *q = d + (size_t)y * dw + x;
+      if (VEC) {
+        *reinterpret_cast<uint32_t *>(q) = out;
+      } else {
+        for (unsigned j = 0; j < 4 && x + j < dw; j++) q[j] = (uint8_t)(out >> (8 * j));
+      }
+    }
   }
 }
 
@@ -99,8 +127,12 @@ int gs_b200_resize_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *
                          unsigned sh, unsigned n, gs_b200_stream s) {
   GSB_ASSERT(dst && src && dw > 0 && dh > 0 && sw > 0 && sh > 0);  // reference :172
   if (n == 0) return 0;
-  dim3 block(32, 8), grid((dw + 31) / 32, (dh + 7) / 8, n < 65535u ? n : 65535u);
-  gsb::k_resize<<<grid, block, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n);
+  dim3 grid((dw + 127) / 128, (dh + 8 * gsb::RS_ROWS - 1) / (8 * gsb::RS_ROWS), n < 65535u ? n : 65535u);
+  GSB_ASSERT(grid.y <= 65535u);
+  if (dw % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0)
+    gsb::k_resize<true><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n);
+  else
+    gsb::k_resize<false><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n);
   GSB_LAUNCHED(1);
   return 0;
 }
