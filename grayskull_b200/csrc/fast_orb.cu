@@ -264,7 +264,14 @@ k_nms_emit(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned
 // written out row-wise.  Arc test on sign bits: funnel-shifting the sign of (hi - v) / (v - lo)
 // into the masks costs one IADD and one SHF per sample and mask.
 // ---------------------------------------------------------------------------------------------
-constexpr int FT_W = 128, FT_H = 16, FT_SW = FT_W + 16, FT_SH = FT_H + 6;   // tile + halo; pitch 144 B = one TMA box row
+constexpr int FT_W = 128, FT_H = 16, FT_SW = FT_W + 32, FT_SH = FT_H + 6;   // 160-B pitch = one TMA box row
+constexpr int FT_X = 16;                                                   // tile byte of the first pixel column
+
+// 4 bytes -> 16-bit lane pairs (b0, b2) and (b1, b3)
+__device__ __forceinline__ void pairs_eo(uint32_t v, uint32_t &e, uint32_t &o) {
+  e = v & 0x00FF00FFu;
+  o = prmt(v, 0, 0x4341);
+}
 
 template <bool TMA>
 __global__ void __launch_bounds__(256)
@@ -272,14 +279,15 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
                    uint8_t *__restrict__ score, unsigned t) {
   __shared__ __align__(128) uint8_t s_src[FT_SH * FT_SW];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ uint8_t s_score[FT_H * FT_W];
+  __shared__ __align__(16) uint8_t s_score[FT_H * FT_W];
   __shared__ uint16_t s_list[FT_H * FT_W];
   __shared__ unsigned s_cnt;
-  const unsigned f = blockIdx.z, tid = threadIdx.x, lane = tid & 31;
-  const int x0 = 3 + blockIdx.x * FT_W, y0 = 3 + blockIdx.y * FT_H;    // first interior pixel of the tile
+  const unsigned f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // tile = pixel columns [x0, x0+128) (x0 a multiple of 128: aligned words), interior rows [y0, y0+16)
+  const int x0 = blockIdx.x * FT_W, y0 = 3 + blockIdx.y * FT_H;
   const uint8_t *img = src + (size_t)f * w * h;
   if (tid == 0) s_cnt = 0;
-  // stage rows y0-3 .. y0+FT_H+2, columns x0-3 .. x0+FT_W+12 (x0 - 3 = 128 * blockIdx.x: 16-B aligned)
+  // stage rows y0-3 .. y0+18, columns x0-16 .. x0+143
   if (TMA) {
     if (tid == 0) {
       mbar_init(&bar, 1);
@@ -288,12 +296,12 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
     __syncthreads();
     if (tid == 0) {
       mbar_expect_tx(&bar, FT_SH * FT_SW);
-      tma_load_3d(s_src, &tmap, (x0 - 3) / 4, y0 - 3, (int)f, &bar);   // out-of-image reads as 0, never used
+      tma_load_3d(s_src, &tmap, (x0 - FT_X) / 4, y0 - 3, (int)f, &bar);   // out-of-image reads as 0, never used
     }
   } else {
     for (int i = tid; i < FT_SH * FT_SW; i += 256) {
       const int r = i / FT_SW, c = i % FT_SW;
-      const int yy = min(y0 - 3 + r, (int)h - 1), xx = min(x0 - 3 + c, (int)w - 1);
+      const int yy = min(y0 - 3 + r, (int)h - 1), xx = min(max(x0 - FT_X + c, 0), (int)w - 1);
       s_src[i] = __ldg(img + (size_t)yy * w + xx);
     }
   }
@@ -301,29 +309,54 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
   if (TMA) mbar_wait(&bar, 0);
   __syncthreads();
 
-  // phase A: compass pre-test for every pixel of the tile.  Thread = column lx, rows ly0, ly0+2, ...
-  // "at least two of the four compass samples are brighter (darker)" is evaluated on the SIGN bits
-  // of hi - v (v - lo): two-or-more-of-four = (a&b) | (c&d) | ((a|b) & (c|d)).
+  // phase A: compass pre-test (any 9-arc contains two of ring positions 0/4/8/12), 4 pixels per
+  // thread on 16-bit lane pairs.  With K = 0x7FFF - t per lane, bit 15 of (v + K - p) is "v > p + t"
+  // and bit 15 of (p + K - v) is "v < p - t"; bit 15 of (0x7FFF + t - p) is the wrap case t > p
+  // (reference :498), where every non-brighter sample counts as darker.  "at least two of four"
+  // = (a&b) | (c&d) | ((a|b) & (c|d)), "at least three" = (a&b&(c|d)) | (c&d&(a|b)), bitwise.
   {
-    const int lx = tid & (FT_W - 1);
-    const bool col_in = x0 + lx + 3 < (int)w;
-    const int ti = (int)t;
-    unsigned flags = 0;                              // bit k: row (tid >> 7) + 2k of this column is a candidate
+    const int lx = 4 * lane;                                // first of this thread's 4 pixel columns
+    const unsigned tc = min(t, 0x7000u);                    // thresholds above 255 all behave alike
+    const uint32_t kb = (0x7FFFu - tc) * 0x10001u, kw = (0x7FFFu + tc) * 0x10001u;
+    unsigned colmask = 0;                                   // interior columns: 3 <= x < w - 3
 #pragma unroll
-    for (int k = 0; k < FT_H / 2; k++) {
-      const int ly = (tid >> 7) + 2 * k;
-      const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + 3);
-      const int p = c[0], hi = p + ti, lo = p - ti;
-      const int v0 = c[-3 * FT_SW], v4 = c[3], v8 = c[3 * FT_SW], v12 = c[-3];
-      const int b0 = hi - v0, b1 = hi - v4, b2 = hi - v8, b3 = hi - v12;      // negative <=> brighter
-      const int d0 = v0 - lo, d1 = v4 - lo, d2 = v8 - lo, d3 = v12 - lo;      // negative <=> darker (no wrap)
-      const int two_b = (b0 & b1) | (b2 & b3) | ((b0 | b1) & (b2 | b3));
-      const int two_d = (d0 & d1) | (d2 & d3) | ((d0 | d1) & (d2 | d3));
-      // wrap (t > p, reference :498): darker = not brighter; two or more darker <=> not (three or more brighter)
-      const int three_b = (b0 & b1 & (b2 | b3)) | (b2 & b3 & (b0 | b1));
-      const int dsel = lo < 0 ? ~three_b : two_d;
-      const bool cand = col_in && y0 + ly + 3 < (int)h && ((two_b | dsel) < 0);
-      flags |= (unsigned)cand << k;
+    for (int j = 0; j < 4; j++) colmask |= (unsigned)(x0 + lx + j >= 3 && x0 + lx + j + 3 < (int)w) << j;
+    unsigned flags = 0;                                     // bit 4k + j: row warp + 8k, pixel j is a candidate
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int ly = warp + 8 * k;
+      const uint32_t *rowc = reinterpret_cast<const uint32_t *>(s_src + (ly + 3) * FT_SW) + (FT_X / 4) + lane;
+      const uint32_t wl = rowc[-1], wc = rowc[0], wr = rowc[1];
+      const uint32_t up = rowc[-3 * (FT_SW / 4)], dn = rowc[3 * (FT_SW / 4)];
+      const uint32_t v12 = __funnelshift_r(wl, wc, 8);      // bytes x-3 .. x
+      const uint32_t v4 = __funnelshift_r(wc, wr, 24);      // bytes x+3 .. x+6
+      uint32_t pe, po, ve[4], vo[4];
+      pairs_eo(wc, pe, po);
+      pairs_eo(up, ve[0], vo[0]);
+      pairs_eo(v4, ve[1], vo[1]);
+      pairs_eo(dn, ve[2], vo[2]);
+      pairs_eo(v12, ve[3], vo[3]);
+      unsigned cbits = 0;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const uint32_t P = hlf ? po : pe;
+        const uint32_t q = kb - P, r = P + kb, wrap = kw - P;
+        uint32_t b[4], d[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t V = hlf ? vo[i] : ve[i];
+          b[i] = V + q;
+          d[i] = r - V;
+        }
+        const uint32_t two_b = (b[0] & b[1]) | (b[2] & b[3]) | ((b[0] | b[1]) & (b[2] | b[3]));
+        const uint32_t two_d = (d[0] & d[1]) | (d[2] & d[3]) | ((d[0] | d[1]) & (d[2] | d[3]));
+        const uint32_t three_b = (b[0] & b[1] & (b[2] | b[3])) | (b[2] & b[3] & (b[0] | b[1]));
+        const uint32_t cand = two_b | (wrap & ~three_b) | (~wrap & two_d);
+        // lanes: hlf 0 -> pixels 0 and 2, hlf 1 -> pixels 1 and 3
+        cbits |= ((cand >> 15) & 1u) << hlf;
+        cbits |= (cand >> 31) << (2 + hlf);
+      }
+      if (y0 + ly + 3 < (int)h) flags |= (cbits & colmask) << (4 * k);
     }
     // one compaction per thread: warp-exclusive scan of the per-thread candidate counts, one
     // shared-memory atomic per warp (candidates are rare: the common case is an all-zero ballot)
@@ -339,9 +372,9 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
       if (lane == 31) base = atomicAdd(&s_cnt, incl);
       base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
       while (flags) {
-        const int k = __ffs(flags) - 1;
+        const int bit = __ffs(flags) - 1;
         flags &= flags - 1;
-        s_list[base++] = (uint16_t)(((tid >> 7) + 2 * k) * FT_W + lx);
+        s_list[base++] = (uint16_t)((warp + 8 * (bit >> 2)) * FT_W + lx + (bit & 3));
       }
     }
   }
@@ -351,7 +384,7 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
   const unsigned ncand = s_cnt;
   for (unsigned k = tid; k < ncand; k += 256) {
     const int i = s_list[k], ly = i / FT_W, lx = i % FT_W;
-    const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + 3);
+    const uint8_t *c = s_src + (ly + 3) * FT_SW + (lx + FT_X);
     const int p = c[0], hi = p + (int)t, lo = p - (int)t;
     unsigned bright = 0, dark = 0;
     int mind = 255;
@@ -373,11 +406,26 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
   }
   __syncthreads();
 
-  // phase C: write the tile's scores (interior pixels only)
-  for (int i = tid; i < FT_H * FT_W; i += 256) {
-    const int ly = i / FT_W, lx = i % FT_W;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x + 3 < (int)w && y + 3 < (int)h) score[(size_t)f * w * h + (size_t)y * w + x] = s_score[i];
+  // phase C: write the tile's scores, interior pixels only (3 <= x < w-3): a word per 4 pixels
+  {
+    const int lx = 4 * lane;
+    unsigned colmask = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) colmask |= (unsigned)(x0 + lx + j >= 3 && x0 + lx + j + 3 < (int)w) << j;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int ly = warp + 8 * k, y = y0 + ly;
+      if (y + 3 >= (int)h || colmask == 0) continue;
+      const uint32_t v = *reinterpret_cast<const uint32_t *>(s_score + ly * FT_W + lx);
+      uint8_t *q = score + (size_t)f * w * h + (size_t)y * w + x0 + lx;
+      if (colmask == 0xF && TMA) {            // (TMA <=> w % 16 == 0 and aligned bases: word stores are aligned)
+        *reinterpret_cast<uint32_t *>(q) = v;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if ((colmask >> j) & 1u) q[j] = (uint8_t)(v >> (8 * j));
+      }
+    }
   }
 }
 
@@ -388,14 +436,15 @@ template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_nms_mask(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h, unsigned mw,
            unsigned *__restrict__ masks, unsigned *__restrict__ rowcount) {
-  __shared__ unsigned wsum[8];
-  const unsigned rows = h - 6, y = 3 + blockIdx.x, f = blockIdx.y;
+  const unsigned rows = h - 6, lane = threadIdx.x & 31;
+  const unsigned row = blockIdx.x * 8 + (threadIdx.x >> 5), f = blockIdx.y;   // one warp per interior row
+  if (row >= rows) return;
+  const unsigned y = 3 + row;
   const uint8_t *sm = score + (size_t)f * sw * sh;
-  unsigned *mrow = masks + ((size_t)f * rows + blockIdx.x) * mw;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned *mrow = masks + ((size_t)f * rows + row) * mw;
   unsigned total = 0;
-  for (unsigned xb = 0; xb < w; xb += 1024) {        // 256 threads x 4 pixels
-    const unsigned x4 = xb + threadIdx.x * 4;
+  for (unsigned xb = 0; xb < w; xb += 128) {         // 32 lanes x 4 pixels
+    const unsigned x4 = xb + lane * 4;
     unsigned nib = 0;
     if (x4 < w) {
       bool any = true;
@@ -414,20 +463,13 @@ k_nms_mask(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned
     m |= __shfl_xor_sync(0xFFFFFFFFu, m, 1);
     m |= __shfl_xor_sync(0xFFFFFFFFu, m, 2);
     m |= __shfl_xor_sync(0xFFFFFFFFu, m, 4);
-    const unsigned word = (x4 >> 5);
+    const unsigned word = x4 >> 5;
     if ((lane & 7) == 0 && word < mw) mrow[word] = m;
     total += __popc(nib);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-  if (lane == 0) wsum[warp] = total;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned t = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) t += wsum[i];
-    rowcount[(size_t)f * rows + blockIdx.x] = t;
-  }
+  if (lane == 0) rowcount[(size_t)f * rows + row] = total;
 }
 
 // emit from the masks: one warp per interior row; rows past the cap or without survivors exit
@@ -675,10 +717,10 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
   if (!rowcount || !masks) return (int)cudaErrorMemoryAllocation;
   GSB_ASSERT(n <= 65535u && rows <= 0x7FFFFFFFu);
   if (sw == w && sh == h && !force_generic()) {
-    dim3 grid((w - 6 + FT_W - 1) / FT_W, (h - 6 + FT_H - 1) / FT_H, n);
+    dim3 grid((w + FT_W - 1) / FT_W, (h - 6 + FT_H - 1) / FT_H, n);
     GSB_ASSERT(grid.y <= 65535u);
     CUtensorMap tmap;
-    if (tma_ok(src, w) && make_tmap_u8frames(&tmap, src, w, h, n, FT_SW / 4, FT_SH))
+    if (tma_ok(src, w) && tma_ok(score, w) && make_tmap_u8frames(&tmap, src, w, h, n, FT_SW / 4, FT_SH))
       k_fast_score_tiled<true><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
     else {
       memset(&tmap, 0, sizeof(tmap));
@@ -690,9 +732,9 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
   }
   GSB_LAUNCHED(1);
   if (sw % 4 == 0 && reinterpret_cast<uintptr_t>(score) % 4 == 0 && sw >= w)
-    k_nms_mask<true><<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
+    k_nms_mask<true><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
   else
-    k_nms_mask<false><<<dim3(rows, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
+    k_nms_mask<false><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
   GSB_LAUNCHED(1);
   k_row_scan<<<n, 1024, 0, s>>>(rowcount, rows, counts, nkps);
   GSB_LAUNCHED(1);
