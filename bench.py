@@ -272,7 +272,7 @@ def gpu_main(args):
         cfg = {"workload": "c3: gs_orb_extract nkps=1250 t=20, 1920x1080 blurred-noise uint8, batch %d per GPU" % n,
                "frames_per_gpu": n, "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (n * h * w / 2**30)}
         kernels = {"gs_orb_extract": (step, 2.0 * n * h * w)}
-        launches_per_step = 6
+        launches_per_step = 8
     elif wl == "c4":
         n, h, w = args.batch or B4, H4, W4
         cas = g.load_cascade()

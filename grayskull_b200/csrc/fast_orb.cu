@@ -30,7 +30,9 @@ namespace gsb {
 
 static int g_trig_mode = 0;
 
-__constant__ uint32_t c_brief[256] = {
+// read with one coalesced 128-byte load per 32 pairs (a __constant__ table indexed per lane would
+// serialise into 32 constant-cache accesses)
+__device__ const uint32_t c_brief[256] = {
 #include "brief_pattern.inc"
 };
 
@@ -648,7 +650,7 @@ __device__ __forceinline__ void brief_words(const uint8_t *img, unsigned w, unsi
   const float cos_a = trig_mode ? sinf(a2) : dev_sinf(a2);
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const uint32_t pk = c_brief[32 * k + lane];
+    const uint32_t pk = __ldg(&c_brief[32 * k + lane]);
     const float p0 = (float)(int)(int8_t)(pk & 0xFF), p1 = (float)(int)(int8_t)((pk >> 8) & 0xFF);
     const float p2 = (float)(int)(int8_t)((pk >> 16) & 0xFF), p3 = (float)(int)(int8_t)(pk >> 24);
     const float dx1 = __fsub_rn(__fmul_rn(p0, cos_a), __fmul_rn(p1, sin_a));
@@ -663,25 +665,113 @@ __device__ __forceinline__ void brief_words(const uint8_t *img, unsigned w, unsi
   }
 }
 
+// gs_orb_extract's describe step in three kernels, so that the (expensive, double-precision) libm
+// restatement runs once per keypoint on one thread instead of redundantly on all 32 lanes of a warp:
+//   k_orb_moments : warp per keypoint -> int32 disc moments (stored in the record's descriptor words 0,1)
+//   k_orb_trig    : thread per keypoint -> angle, sin, cos  (angle in place, sin/cos in descriptor words 2,3)
+//   k_orb_brief   : warp per keypoint -> BRIEF-256, final record
 __global__ void __launch_bounds__(256)
-k_orb_describe(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__restrict__ kps,
-               const unsigned *__restrict__ counts, unsigned nkps, unsigned n, int trig_mode) {
+k_orb_moments(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__restrict__ kps,
+              const unsigned *__restrict__ counts, unsigned nkps, unsigned n) {
   const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
   if (gw >= (unsigned long long)n * nkps) return;
   const unsigned f = (unsigned)(gw / nkps), j = (unsigned)(gw % nkps);
   if (j >= counts[f]) return;
   KpRec *k = kps + (size_t)f * nkps + j;
+  int m01, m10;
+  disc_moments15(src + (size_t)f * w * h, w, (int)k->w[0], (int)k->w[1], lane, m01, m10);
+  if (lane == 0) k->w[4] = (uint32_t)m01, k->w[5] = (uint32_t)m10;
+}
+
+__global__ void __launch_bounds__(256)
+k_orb_trig(KpRec *__restrict__ kps, const unsigned *__restrict__ counts, unsigned nkps, unsigned n, int trig_mode) {
+  const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (unsigned long long)n * nkps) return;
+  const unsigned f = (unsigned)(g / nkps), j = (unsigned)(g % nkps);
+  if (j >= counts[f]) return;
+  KpRec *k = kps + (size_t)f * nkps + j;
+  const float angle = orient_from_moments((int)k->w[4], (int)k->w[5], trig_mode);
+  const float a2 = __fadd_rn(angle, 1.57079f);       // the reference's 6-digit pi/2 (:626)
+  const float sin_a = trig_mode ? sinf(angle) : dev_sinf(angle);
+  const float cos_a = trig_mode ? sinf(a2) : dev_sinf(a2);
+  k->w[3] = __float_as_uint(angle);
+  k->w[6] = __float_as_uint(sin_a), k->w[7] = __float_as_uint(cos_a);
+}
+
+// BRIEF-256 with given sin/cos (reference :628-636); each ballot is one descriptor word
+__device__ __forceinline__ void brief_words_sc(const uint8_t *img, unsigned w, unsigned h, int x, int y, float sin_a,
+                                               float cos_a, unsigned lane, uint32_t (&desc)[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t pk = __ldg(&c_brief[32 * k + lane]);
+    const float p0 = (float)(int)(int8_t)(pk & 0xFF), p1 = (float)(int)(int8_t)((pk >> 8) & 0xFF);
+    const float p2 = (float)(int)(int8_t)((pk >> 16) & 0xFF), p3 = (float)(int)(int8_t)(pk >> 24);
+    const float dx1 = __fsub_rn(__fmul_rn(p0, cos_a), __fmul_rn(p1, sin_a));
+    const float dy1 = __fadd_rn(__fmul_rn(p0, sin_a), __fmul_rn(p1, cos_a));
+    const float dx2 = __fsub_rn(__fmul_rn(p2, cos_a), __fmul_rn(p3, sin_a));
+    const float dy2 = __fadd_rn(__fmul_rn(p2, sin_a), __fmul_rn(p3, cos_a));
+    const unsigned x1 = (unsigned)(x + __float2int_rz(dx1)), y1 = (unsigned)(y + __float2int_rz(dy1));
+    const unsigned x2 = (unsigned)(x + __float2int_rz(dx2)), y2 = (unsigned)(y + __float2int_rz(dy2));
+    const unsigned i1 = (x1 < w && y1 < h) ? __ldg(img + (size_t)y1 * w + x1) : 0u;
+    const unsigned i2 = (x2 < w && y2 < h) ? __ldg(img + (size_t)y2 * w + x2) : 0u;
+    desc[k] = __ballot_sync(0xFFFFFFFFu, i1 > i2);
+  }
+}
+
+// The 512 samples of a descriptor lie within +-22 px of the keypoint (pattern offsets <= 15 per axis,
+// any rotation).  The warp stages that 45-row x 48-byte patch in shared memory with coalesced word
+// loads (zeros outside the image = gs_get's out-of-bounds value) and gathers from there.
+constexpr int BP_R = 22, BP_ROWS = 2 * BP_R + 1, BP_PITCH = 48;
+
+template <bool STAGED>
+__global__ void __launch_bounds__(256)
+k_orb_brief(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__restrict__ kps,
+            const unsigned *__restrict__ counts, unsigned nkps, unsigned n) {
+  __shared__ __align__(16) uint8_t s_patch[STAGED ? 8 : 1][BP_ROWS * BP_PITCH];
+  const unsigned long long gw = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (gw >= (unsigned long long)n * nkps) return;
+  const unsigned f = (unsigned)(gw / nkps), j = (unsigned)(gw % nkps);
+  if (j >= counts[f]) return;
+  KpRec *k = kps + (size_t)f * nkps + j;
   const uint8_t *img = src + (size_t)f * w * h;
   const int x = (int)k->w[0], y = (int)k->w[1];
-  int m01, m10;
-  disc_moments15(img, w, x, y, lane, m01, m10);
-  const float angle = orient_from_moments(m01, m10, trig_mode);
+  const float sin_a = __uint_as_float(k->w[6]), cos_a = __uint_as_float(k->w[7]);
   uint32_t desc[8];
-  brief_words(img, w, h, x, y, angle, lane, trig_mode, desc);
+  if (!STAGED) {
+    brief_words_sc(img, w, h, x, y, sin_a, cos_a, lane, desc);
+  } else {
+    uint8_t *patch = s_patch[warp];
+    const int xa = (x - BP_R) & ~3;                      // patch byte 0 <-> image column xa (w % 4 == 0)
+    for (int i = lane; i < BP_ROWS * (BP_PITCH / 4); i += 32) {
+      const int r = i / (BP_PITCH / 4), c = i % (BP_PITCH / 4);
+      const int yy = y - BP_R + r, xx = xa + 4 * c;
+      uint32_t v = 0;
+      if (yy >= 0 && yy < (int)h && xx >= 0 && xx < (int)w) v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)yy * w + xx));
+      reinterpret_cast<uint32_t *>(patch)[i] = v;
+    }
+    __syncwarp();
+    const int ox = x - xa;                               // keypoint column inside the patch
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+      const uint32_t pk = __ldg(&c_brief[32 * kk + lane]);
+      const float p0 = (float)(int)(int8_t)(pk & 0xFF), p1 = (float)(int)(int8_t)((pk >> 8) & 0xFF);
+      const float p2 = (float)(int)(int8_t)((pk >> 16) & 0xFF), p3 = (float)(int)(int8_t)(pk >> 24);
+      const int dx1 = __float2int_rz(__fsub_rn(__fmul_rn(p0, cos_a), __fmul_rn(p1, sin_a)));
+      const int dy1 = __float2int_rz(__fadd_rn(__fmul_rn(p0, sin_a), __fmul_rn(p1, cos_a)));
+      const int dx2 = __float2int_rz(__fsub_rn(__fmul_rn(p2, cos_a), __fmul_rn(p3, sin_a)));
+      const int dy2 = __float2int_rz(__fadd_rn(__fmul_rn(p2, sin_a), __fmul_rn(p3, cos_a)));
+      // |d| <= 22 always (sqrt(2) * 15 = 21.2); the clamp only keeps a hypothetical outlier in bounds
+      const int c1 = min(max(dx1, -BP_R), BP_R) + ox, r1 = min(max(dy1, -BP_R), BP_R) + BP_R;
+      const int c2 = min(max(dx2, -BP_R), BP_R) + ox, r2 = min(max(dy2, -BP_R), BP_R) + BP_R;
+      const unsigned i1 = patch[r1 * BP_PITCH + c1], i2 = patch[r2 * BP_PITCH + c2];
+      desc[kk] = __ballot_sync(0xFFFFFFFFu, i1 > i2);
+    }
+  }
+  __syncwarp();
   if (lane == 0) {
     uint4 *o = reinterpret_cast<uint4 *>(k);
-    o[0] = make_uint4(k->w[0], k->w[1], k->w[2], __float_as_uint(angle));
     o[1] = make_uint4(desc[0], desc[1], desc[2], desc[3]);
     o[2] = make_uint4(desc[4], desc[5], desc[6], desc[7]);
   }
@@ -779,9 +869,14 @@ int gs_b200_orb_extract_batch(const uint8_t *src, unsigned w, unsigned h, unsign
   const unsigned long long warps = (unsigned long long)n * nkps;
   const unsigned long long blocks = (warps + 7) / 8;
   GSB_ASSERT(blocks < 0x7FFFFFFFull);
-  gsb::k_orb_describe<<<(unsigned)blocks, 256, 0, st>>>(src, w, h, reinterpret_cast<gsb::KpRec *>(kps), counts, nkps, n,
-                                                        gsb::g_trig_mode);
-  GSB_LAUNCHED(1);
+  gsb::KpRec *kr = reinterpret_cast<gsb::KpRec *>(kps);
+  gsb::k_orb_moments<<<(unsigned)blocks, 256, 0, st>>>(src, w, h, kr, counts, nkps, n);
+  gsb::k_orb_trig<<<(unsigned)((warps + 255) / 256), 256, 0, st>>>(kr, counts, nkps, n, gsb::g_trig_mode);
+  if (w % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0 && !gsb::force_generic())
+    gsb::k_orb_brief<true><<<(unsigned)blocks, 256, 0, st>>>(src, w, h, kr, counts, nkps, n);
+  else
+    gsb::k_orb_brief<false><<<(unsigned)blocks, 256, 0, st>>>(src, w, h, kr, counts, nkps, n);
+  GSB_LAUNCHED(3);
   return 0;
 }
 
