@@ -294,6 +294,35 @@ def gpu_main(args):
         kernels = {"gs_integral": (lambda: api.integral_batch(src, out=ii), 5.0 * n * h * w),
                    "gs_lbp_detect": (lambda: api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2), 4.0 * n * h * w)}
         launches_per_step = 5
+    elif wl == "c5":
+        # BASELINE configs[4]: blur -> sobel -> FAST/ORB -> integral + LBP on 1920x1080 frames, sharded by frame
+        # (each rank owns its own frames; 8192 frames over 8 GPUs = 1024 per GPU).  FAST and LBP both run on
+        # the sobel output.
+        n, h, w = args.batch or 256, H3, W3
+        cas = g.load_cascade()
+        src = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=dev)
+        blur = torch.empty_like(src)
+        sob = torch.zeros_like(src)
+        sm = torch.zeros_like(src)
+        ii = torch.empty((n, h, w), dtype=torch.int32, device=dev)
+
+        def step():
+            api.blur_batch(src, R2, out=blur)
+            api.sobel_batch(blur, out=sob)
+            api.orb_extract_batch(sob, NK3, T3, scoremap=sm)
+            api.integral_batch(sob, out=ii)
+            api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2)
+
+        units_per_step = n * h * w
+        unit, scale, metric = "Mpixels/s", 1e-6, "Mpixels/s, pipeline blur(r=5) -> sobel -> gs_orb_extract -> gs_integral + gs_lbp_detect, 1920x1080 uint8"
+        cfg = {"workload": "c5: blur r=5 -> sobel -> orb_extract(nkps=1250,t=20) -> integral + lbp_detect(sf 1.1, scales 1..4, step 2), 1920x1080, %d frames per GPU" % n,
+               "frames_per_gpu": n, "l2": "inputs (%.1f GiB per GPU) exceed the 126 MB L2" % (n * h * w / 2**30)}
+        kernels = {"gs_blur_r5": (lambda: api.blur_batch(src, R2, out=blur), 2.0 * n * h * w),
+                   "gs_sobel": (lambda: api.sobel_batch(blur, out=sob), 2.0 * n * h * w),
+                   "gs_orb_extract": (lambda: api.orb_extract_batch(sob, NK3, T3, scoremap=sm), 2.0 * n * h * w),
+                   "gs_integral": (lambda: api.integral_batch(sob, out=ii), 5.0 * n * h * w),
+                   "gs_lbp_detect": (lambda: api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2), 4.0 * n * h * w)}
+        launches_per_step = 14
     elif wl == "ops":
         # per-op table (every stencil / resampling op of the path at 4096x4096), not a driver line
         n, h, w = args.batch or 64, H2, W2
@@ -403,7 +432,7 @@ def gpu_main(args):
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and wl in ("c2", "c3", "c4"):
         _, cpu = cpu_reference(wl, steps=1, warmup=0, max_cores=args.cpu_cores or None)
 
     if rank == 0:
@@ -441,7 +470,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "ops"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "ops"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
     ap.add_argument("--e2e-frames", type=int, default=64)

@@ -331,3 +331,25 @@ def test_c4_integral_lbp_2160p(G, O, cas):
     got = G.rects_to_numpy(rects, counts)[0]
     want = o_detect(O, cas, want_ii, 65536, 1.1, 1.0, 4.0, 2)
     assert got.tobytes() == want.tobytes(), (len(got), len(want))
+
+
+def test_c5_pipeline_composition(G, O, cas):
+    """config C5 shape of work on small frames: blur -> sobel -> ORB and integral + LBP on the sobel
+    output, every stage consuming the previous stage's device buffer, against the oracle chain"""
+    import torch
+    frames = np.stack([L.natural_like(320, 240, 90 + i) for i in range(3)])
+    src = dev(frames)
+    blur = G.blur_batch(src, 5)
+    sob = G.sobel_batch(blur)
+    _, kps, kc = G.orb_extract_batch(sob, 300, 20)
+    ii = G.integral_batch(sob)
+    rects, rc = G.lbp_detect_batch(cas, ii, 1000, 1.1, 1.0, 4.0, 2)
+    gk, gr = G.kps_to_numpy(kps, kc), G.rects_to_numpy(rects, rc)
+    for i in range(3):
+        b = o_blur(O, frames[i], 5)
+        s = o_sobel(O, b)
+        assert np.array_equal(sob[i].cpu().numpy(), s)
+        assert gk[i].tobytes() == o_orb(O, s, np.zeros_like(s), 300, 20).tobytes()
+        t = o_integral(O, s)
+        assert np.array_equal(ii[i].cpu().numpy().view(np.uint32), t)
+        assert gr[i].tobytes() == o_detect(O, cas, t, 1000, 1.1, 1.0, 4.0, 2).tobytes()
