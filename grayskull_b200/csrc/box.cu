@@ -18,10 +18,12 @@
 //      sums for two adjacent pixels are formed on 16-bit lane pairs from a rolling sum of pair
 //      words (4 integer ops per 2 pixels, radius independent); max (2*7+1)^2*255 = 57375 < 65536;
 //   3. exact division without integer divide: with m = ceil(2^24 / count),
-//        fma_rd(2^23 + S, m * 2^-24, 2^23 - m/2) = 2^23 + floor(S * m / 2^24)
+//        fma_rd(float(S), m * 2^-24, 2^23) = 2^23 + floor(S * m / 2^24)
 //      is computed exactly before its single round-down, and floor(S*m/2^24) == S / count for
 //      all S <= 255 * count, count <= 225 (checked exhaustively in tests/test_host_logic.py);
-//      the quotient is the low byte of the float's bit pattern.  Tiles whose windows all lie
+//      the quotient is the low byte of the float's bit pattern.  float(S) comes straight from
+//      either 16-bit half on the conversion pipe (I2F.U16): the kernel was ALU-pipe bound, so the
+//      byte packing and the lane-total broadcast are multiply-adds (FMA pipe) for the same reason.  Tiles whose windows all lie
 //      inside the image use compile-time constants for count = (2r+1)^2 on a branch-free path,
 //      clipped pixels a 226-entry table.
 // Other radii / widths take the generic kernel (one thread per pixel, any radius).

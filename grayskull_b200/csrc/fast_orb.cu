@@ -199,63 +199,9 @@ __device__ __forceinline__ bool nms_keep(const uint8_t *sm, unsigned sw, unsigne
          sm_get(sm, sw, sh, x, y + 1) <= s && sm_get(sm, sw, sh, x + 1, y + 1) <= s;
 }
 
-// one CTA per (interior row, frame): number of NMS survivors in that row
-__global__ void __launch_bounds__(256)
-k_nms_count(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h,
-            unsigned *__restrict__ rowcount) {
-  const unsigned rows = h - 6, y = 3 + blockIdx.x, f = blockIdx.y;
-  const uint8_t *sm = score + (size_t)f * sw * sh;
-  unsigned total = 0;
-  for (unsigned xb = 3; xb + 3 < w; xb += 256) {
-    const unsigned x = xb + threadIdx.x;
-    unsigned s;
-    const bool keep = (x + 3 < w) && nms_keep(sm, sw, sh, x, y, s);
-    total += __syncthreads_count(keep);
-  }
-  if (threadIdx.x == 0) rowcount[(size_t)f * rows + blockIdx.x] = total;
-}
-
 struct KpRec {  // struct gs_keypoint, 48 bytes
   uint32_t w[12];
 };
-
-__global__ void __launch_bounds__(256)
-k_nms_emit(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, unsigned w, unsigned h,
-           const unsigned *__restrict__ rowoff, KpRec *__restrict__ kps, unsigned nkps) {
-  __shared__ unsigned wcnt[8];
-  const unsigned rows = h - 6, y = 3 + blockIdx.x, f = blockIdx.y;
-  unsigned base = rowoff[(size_t)f * rows + blockIdx.x];
-  if (base >= nkps) return;
-  const uint8_t *sm = score + (size_t)f * sw * sh;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (unsigned xb = 3; xb + 3 < w; xb += 256) {
-    const unsigned x = xb + threadIdx.x;
-    unsigned s = 0;
-    const bool keep = (x + 3 < w) && nms_keep(sm, sw, sh, x, y, s);
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (lane == 0) wcnt[warp] = __popc(bal);
-    __syncthreads();
-    unsigned before = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const unsigned c = wcnt[i];
-      before += (i < (int)warp) ? c : 0;
-      total += c;
-    }
-    const unsigned pos = base + before + __popc(bal & ((1u << lane) - 1u));
-    if (keep && pos < nkps) {
-      KpRec r;
-      r.w[0] = x, r.w[1] = y, r.w[2] = s;
-#pragma unroll
-      for (int i = 3; i < 12; i++) r.w[i] = 0;  // angle 0.0f, descriptor {0} (reference :530)
-      uint4 *o = reinterpret_cast<uint4 *>(kps + (size_t)f * nkps + pos);
-      o[0] = make_uint4(r.w[0], r.w[1], r.w[2], 0), o[1] = make_uint4(0, 0, 0, 0), o[2] = make_uint4(0, 0, 0, 0);
-    }
-    base += total;
-    if (base >= nkps) return;  // uniform
-    __syncthreads();
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Tiled FAST score (used when the score map has the image's size): a CTA owns a 128 x 16 pixel

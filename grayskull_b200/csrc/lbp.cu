@@ -8,7 +8,7 @@
 //             the per-scale truncated feature geometry (int)(int8 * scale) (:799-804) are computed
 //             on the host with the reference's exact fp32 operations and cached on the device,
 //             together with the cascade tables (keyed by content hash);
-//   k_lbp_scan2  : a CTA owns 2048 consecutive windows of ONE scale (64 "slots" of 32 x-adjacent
+//   k_lbp_scan2  : a CTA owns 4096 consecutive windows of ONE scale (128 "slots" of 32 x-adjacent
 //             windows).  The cascade tables and that scale's feature geometry (precomputed 32-bit
 //             row / column offsets of the 4x4 corner lattice: 16 loads per weak instead of the
 //             reference's 36, one IADD per address) live in shared memory.  Windows run the cascade
@@ -19,7 +19,7 @@
 //             bit per window, which keeps the reference's order for free;
 //   k_lbp_scan   : round-1 kernel (lane per window, ballot early exit), kept for cascades whose
 //             tables do not fit shared memory or whose features leave their window;
-//   k_row_scan   : per-frame exclusive scan of the per-CTA hit counts;
+//   k_lbp_count / k_row_scan : hits per 256-window block and their per-frame exclusive scan;
 //   k_lbp_emit   : rects written in the reference's (scale, y, x) order, truncated at max_rects
 //             (the reference stops scanning there, :819-823).
 #include <mutex>
