@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the grayskull hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|ops] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5|ops|match] [--impl reference]
 
 Default workload = BASELINE.json configs[1] ("c2"): gs_blur r=5 + gs_sobel on 4096x4096 synthetic
 uint8 frames, batch 256 per GPU (weak scaling: every rank processes its own 256 frames; frames are
@@ -323,6 +323,30 @@ def gpu_main(args):
                    "gs_integral": (lambda: api.integral_batch(sob, out=ii), 5.0 * n * h * w),
                    "gs_lbp_detect": (lambda: api.lbp_detect_batch(cas, ii, 65536, 1.1, 1.0, 4.0, 2), 4.0 * n * h * w)}
         launches_per_step = 14
+    elif wl == "match":
+        # gs_match_orb over frame pairs (1250 x 1250 descriptors each, the c3 keypoint budget).
+        # Not HBM-bound: 8 POPC per descriptor comparison on the 16-lane/clk/SM POPC path bounds it.
+        npairs, nd = args.batch or 2048, NK3
+        gen = torch.Generator(device=dev); gen.manual_seed(77 + rank)
+        k2 = torch.randint(-2**31, 2**31 - 1, (npairs, nd, 12), dtype=torch.int32, device=dev, generator=gen)
+        k1 = k2[:, torch.randperm(nd, device=dev)].clone()
+        flip = (torch.rand((npairs, nd, 8), device=dev, generator=gen) < 0.6).to(torch.int32) << torch.randint(0, 31, (npairs, nd, 8), device=dev, generator=gen).to(torch.int32)
+        k1[:, :, 4:] ^= flip                     # near-duplicates: ~5 flipped bits per descriptor
+        k1[:, nd // 2:, 4:] = torch.randint(-2**31, 2**31 - 1, (npairs, nd - nd // 2, 8), dtype=torch.int32, device=dev, generator=gen)
+        del flip
+        cnt = torch.full((npairs,), nd, dtype=torch.int32, device=dev)
+        src = k1
+        n, h, w = npairs, nd, nd
+
+        def step():
+            api.match_orb_batch(k1, cnt, k2, cnt, nd, 60.0)
+
+        units_per_step = npairs * nd * nd
+        unit, scale, metric = "Gcomparisons/s", 1e-9, "256-bit descriptor comparisons/s, gs_match_orb 1250 x 1250 per frame pair"
+        cfg = {"workload": "match: gs_match_orb max_distance=60, 1250 x 1250 descriptors per pair, %d pairs per GPU" % npairs,
+               "pairs_per_gpu": npairs, "l2": "descriptor sets (%.0f MB per GPU) exceed the 126 MB L2" % (2 * npairs * nd * 48 / 1e6)}
+        kernels = {"gs_match_orb": (step, 2.0 * npairs * nd * 48 + 12.0 * npairs * nd)}
+        launches_per_step = 2
     elif wl == "ops":
         # per-op table (every stencil / resampling op of the path at 4096x4096), not a driver line
         n, h, w = args.batch or 64, H2, W2
@@ -434,11 +458,24 @@ def gpu_main(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and wl in ("c2", "c3", "c4"):
         _, cpu = cpu_reference(wl, steps=1, warmup=0, max_cores=args.cpu_cores or None)
+    if rank == 0 and world == 1 and not args.no_cpu and wl == "match":
+        import numpy as np
+        import _libs as L
+        kind = "reference" if L.have_ref() else "port"
+        fn = L.ref().gs_match_orb if kind == "reference" else L.oracle().gso_match_orb
+        a = api.kps_to_numpy(k1[:1], cnt[:1])[0]; b = api.kps_to_numpy(k2[:1], cnt[:1])[0]
+        m = np.zeros(nd, L.MATCH_DTYPE)
+        t0 = time.perf_counter(); reps = 0
+        while time.perf_counter() - t0 < 5.0:
+            fn(L.ptr(a), nd, L.ptr(b), nd, L.ptr(m), nd, 60.0); reps += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": reps * nd * nd / dt * scale, "unit": unit, "cores": 1, "kind": kind,
+               "sample": "%d calls of gs_match_orb on one 1250 x 1250 pair (gcc -std=c99 -O2, single thread)" % reps}
 
     if rank == 0:
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "u8" if wl != "c4" else "u32", "data": "synthetic (uniform iid u8, torch.randint; c3/c4: gs_blur r=3 of it)", "config": cfg, "clocks": clocks,
+               "dtype": {"c4": "u32", "match": "u32 (xor + popc)"}.get(wl, "u8"), "data": "synthetic (uniform iid u8, torch.randint; c3/c4: gs_blur r=3 of it)", "config": cfg, "clocks": clocks,
                "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
                "roofline": roofline, "kernels": kres, "cpu_baseline": cpu,
                "tma_path": bool(lib.gs_b200_uses_tma(w, h, src.data_ptr()))}
@@ -470,7 +507,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "ops"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "ops", "match"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
     ap.add_argument("--e2e-frames", type=int, default=64)

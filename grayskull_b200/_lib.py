@@ -37,6 +37,7 @@ class Cascade(C.Structure):  # struct gs_lbp_cascade, reference grayskull.h:54-6
 KP_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("response", "<u4"), ("angle", "<f4"),
                      ("descriptor", "<u4", (8,))])
 RECT_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("w", "<u4"), ("h", "<u4")])
+MATCH_DTYPE = np.dtype([("idx1", "<u4"), ("idx2", "<u4"), ("distance", "<u4")])
 
 _u, _i, _f, _p, _sz = C.c_uint, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "gs_compute_orientation": (_f, [Image, _u, _u, _u]),
     "gs_brief_descriptor": (None, [Image, _p]),
     "gs_orb_extract": (_u, [Image, _p, _u, _u, _p]),
+    "gs_match_orb": (_u, [_p, _u, _p, _u, _p, _u, _f]),
     "gs_lbp_window": (_u, [_p, _p, _u, _u, _i, _i, _f]),
     "gs_lbp_detect": (_u, [_p, _p, _u, _u, _p, _u, _f, _f, _f, _i]),
     # include/grayskull_b200.h
@@ -86,6 +88,7 @@ SIGNATURES = {
     "gs_b200_fast_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_orb_extract_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_set_trig_mode": (None, [_i]),
+    "gs_b200_match_orb_batch": (_i, [_p, _p, _u, _p, _p, _u, _u, _p, _p, _u, _f, _p]),
     "gs_b200_lbp_detect_batch": (_i, [_p, _p, _u, _u, _u, _p, _p, _u, _f, _f, _f, _i, _p]),
     "gs_b200_lbp_window_count": (C.c_ulonglong, [_p, _u, _u, _f, _f, _f, _i]),
 }

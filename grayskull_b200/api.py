@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import lib, check, Image, KP_DTYPE, RECT_DTYPE
+from ._lib import lib, check, Image, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE
 
 
 def _img(a):
@@ -77,6 +77,14 @@ def gs_orb_extract(img, nkps, threshold, scoremap_buffer):
     kps = np.zeros(nkps, KP_DTYPE)
     n = lib().gs_orb_extract(_img(img), _vp(kps), nkps, threshold, _vp(scoremap_buffer))
     return kps[:n]
+
+
+def gs_match_orb(kps1, kps2, max_matches, max_distance):
+    """kps1, kps2: KP_DTYPE arrays -> MATCH_DTYPE array (reference gs_match_orb)"""
+    m = np.zeros(max(max_matches, 1), MATCH_DTYPE)
+    k2 = kps2 if len(kps2) else np.zeros(1, KP_DTYPE)
+    n = lib().gs_match_orb(_vp(kps1), len(kps1), _vp(k2), len(kps2), _vp(m), max_matches, max_distance)
+    return m[:n]
 
 
 def gs_lbp_window(cascade, ii, x, y, scale):
@@ -198,6 +206,18 @@ def orb_extract_batch(src, nkps, threshold, scoremap=None):
     check(lib().gs_b200_orb_extract_batch(_p(src), w, h, n, _p(scoremap), _p(kps), _p(counts), nkps,
                                           threshold, _stream()), "orb_extract_batch")
     return scoremap, kps, counts
+
+
+def match_orb_batch(kps1, counts1, kps2, counts2, max_matches, max_distance):
+    """kps*: (npairs, stride, 12) int32 keypoint words as produced by orb_extract_batch, counts*: (npairs,)
+    -> (matches[npairs, max_matches, 3], counts[npairs])"""
+    import torch
+    npairs, s1, s2 = kps1.shape[0], kps1.shape[1], kps2.shape[1]
+    matches = torch.empty((npairs, max_matches, 3), dtype=torch.int32, device=kps1.device)
+    counts = torch.empty((npairs,), dtype=torch.int32, device=kps1.device)
+    check(lib().gs_b200_match_orb_batch(_p(kps1), _p(counts1), s1, _p(kps2), _p(counts2), s2, npairs, _p(matches),
+                                        _p(counts), max_matches, max_distance, _stream()), "match_orb_batch")
+    return matches, counts
 
 
 def lbp_detect_batch(cascade, ii, max_rects, scale_factor, min_scale, max_scale, step):

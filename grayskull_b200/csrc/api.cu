@@ -203,6 +203,28 @@ unsigned gs_orb_extract(struct gs_image img, struct gs_keypoint *kps, unsigned n
   return c;
 }
 
+unsigned gs_match_orb(const struct gs_keypoint *kps1, unsigned n1, const struct gs_keypoint *kps2, unsigned n2,
+                      struct gs_match *matches, unsigned max_matches, float max_distance) {
+  GSB_ASSERT(kps1 && kps2 && matches);  // reference :683
+  if (n1 == 0 || max_matches == 0) return 0;
+  Buf a = in_buf(kps1, sizeof(struct gs_keypoint) * (size_t)n1, gsb::WS_STAGE_A);
+  Buf b = in_buf(n2 ? kps2 : nullptr, sizeof(struct gs_keypoint) * (size_t)n2, gsb::WS_STAGE_B);
+  Buf m = in_buf(matches, sizeof(struct gs_match) * (size_t)max_matches, gsb::WS_STAGE_C, false);
+  unsigned *ctl = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!ctl) die("device workspace allocation", 1);
+  const unsigned hn[2] = {n1, n2};
+  GS_CUDA(cudaMemcpyAsync(ctl, hn, sizeof(hn), cudaMemcpyHostToDevice, 0));
+  const struct gs_keypoint *k2 = n2 ? (const struct gs_keypoint *)b.dev : (const struct gs_keypoint *)a.dev;
+  GS_DO(gs_b200_match_orb_batch((const struct gs_keypoint *)a.dev, ctl, n1, k2, ctl + 1, n2 ? n2 : 1, 1,
+                                (struct gs_match *)m.dev, ctl + 2, max_matches, max_distance, 0));
+  unsigned c = 0;
+  GS_CUDA(cudaMemcpyAsync(&c, ctl + 2, sizeof(c), cudaMemcpyDeviceToHost, 0));
+  finish();
+  out_buf(m, sizeof(struct gs_match) * (size_t)c);
+  finish();
+  return c;
+}
+
 unsigned gs_lbp_window(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw, unsigned ih, int x, int y,
                        float scale) {
   GSB_ASSERT(c && ii);

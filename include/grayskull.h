@@ -43,6 +43,7 @@
 #define gs_orb_extract gs_cpu_orb_extract
 #define gs_lbp_window gs_cpu_lbp_window
 #define gs_lbp_detect gs_cpu_lbp_detect
+#define gs_match_orb gs_cpu_match_orb
 #include GS_UPSTREAM_HEADER
 #undef gs_blur
 #undef gs_sobel
@@ -58,6 +59,7 @@
 #undef gs_orb_extract
 #undef gs_lbp_window
 #undef gs_lbp_detect
+#undef gs_match_orb
 
 #else
 /* ---- stand-alone mode --------------------------------------------------------------- */
@@ -88,6 +90,10 @@ struct gs_keypoint {
   unsigned response;
   float angle;
   uint32_t descriptor[8];
+};
+struct gs_match {
+  unsigned idx1, idx2;
+  unsigned distance;
 };
 struct gs_lbp_cascade {
   uint16_t window_w, window_h;
@@ -190,6 +196,11 @@ unsigned gs_lbp_window(const struct gs_lbp_cascade *c, const unsigned *ii, unsig
 unsigned gs_lbp_detect(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw,
                        unsigned ih, struct gs_rect *rects, unsigned max_rects,
                        float scale_factor, float min_scale, float max_scale, int step);
+
+/* brute-force Hamming matching of ORB descriptors with the 0.8 ratio test, matches in query order
+ * capped at max_matches -- grayskull.h:680-699 (first "next" item after the hot path) */
+unsigned gs_match_orb(const struct gs_keypoint *kps1, unsigned n1, const struct gs_keypoint *kps2, unsigned n2,
+                      struct gs_match *matches, unsigned max_matches, float max_distance);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,14 @@ int gs_b200_orb_extract_batch(const uint8_t *src, unsigned w, unsigned h, unsign
  *              may differ where a rotated offset sits on an integer boundary). */
 void gs_b200_set_trig_mode(int mode);
 
+/* gs_match_orb, reference grayskull.h:680-699, over npairs (set1, set2) pairs.  Pair p's sets start
+ * at kps1 + p*stride1 / kps2 + p*stride2 and hold n1[p] / n2[p] keypoints (e.g. the output layout of
+ * gs_b200_orb_extract_batch: stride = nkps, n = counts); matches: npairs x max_matches records. */
+int gs_b200_match_orb_batch(const struct gs_keypoint *kps1, const unsigned *n1, unsigned stride1,
+                            const struct gs_keypoint *kps2, const unsigned *n2, unsigned stride2,
+                            unsigned npairs, struct gs_match *matches, unsigned *counts,
+                            unsigned max_matches, float max_distance, gs_b200_stream s);
+
 /* ---- LBP cascade ------------------------------------------------------------------------ */
 /* gs_lbp_detect, reference grayskull.h:815-835, over n integral images (device, n*iw*ih
  * uint32).  `c` is a HOST struct (its tables are uploaded once and cached by content).

@@ -430,6 +430,57 @@ GSO_API unsigned gso_orb_extract(const uint8_t *img, unsigned w, unsigned h,
 }
 
 /* ------------------------------------------------------------------------------------------
+ * gs_match_orb, grayskull.h:671-699.  For query i the reference's sequential scan
+ * keeps the two smallest Hamming distances of the multiset {d_j} U {M, M}, M = max_distance + 1
+ * (fp32), best_idx = the first j attaining the smallest (0 if none is below M); a match is emitted
+ * when best <= max_distance and best < 0.8f * second (fp32 product), in query order, until
+ * max_matches.  Restated with an order-free two-minimum merge (what the GPU's lanes do).
+ * ---------------------------------------------------------------------------------------- */
+struct gso_match {
+  unsigned idx1, idx2, distance;
+};
+static unsigned hamming256(const uint32_t *a, const uint32_t *b) {
+  unsigned d = 0;
+  for (int i = 0; i < 8; i++) d += (unsigned)__builtin_popcount(a[i] ^ b[i]);
+  return d;
+}
+GSO_API unsigned gso_match_orb(const struct gs_keypoint *k1, unsigned n1, const struct gs_keypoint *k2, unsigned n2,
+                               struct gso_match *matches, unsigned max_matches, float max_distance) {
+  unsigned n = 0;
+  const float M = max_distance + 1;
+  for (unsigned i = 0; i < n1 && n < max_matches; i++) {
+    /* four interleaved partial scans (as GPU lanes would), merged afterwards */
+    float best[4], second[4];
+    unsigned bidx[4];
+    for (int l = 0; l < 4; l++) best[l] = M, second[l] = M, bidx[l] = 0xFFFFFFFFu;
+    for (unsigned j = 0; j < n2; j++) {
+      const int l = (int)(j & 3);
+      const float d = (float)hamming256(k1[i].descriptor, k2[j].descriptor);
+      if (d < best[l]) second[l] = best[l], best[l] = d, bidx[l] = j;
+      else if (d < second[l]) second[l] = d;
+    }
+    float b = M, s = M;
+    unsigned bi = 0xFFFFFFFFu;
+    for (int l = 0; l < 4; l++) {
+      /* merge (b, bi, s) with (best[l], bidx[l], second[l]) */
+      float nb, ns, loser;
+      unsigned ni;
+      if (best[l] < b || (best[l] == b && bidx[l] < bi)) nb = best[l], ni = bidx[l], loser = b;
+      else nb = b, ni = bi, loser = best[l];
+      ns = loser < s ? loser : s;
+      ns = second[l] < ns ? second[l] : ns;
+      b = nb, bi = ni, s = ns;
+    }
+    if (bi == 0xFFFFFFFFu) bi = 0;
+    if (b <= max_distance && b < 0.8f * s) {
+      matches[n].idx1 = i, matches[n].idx2 = bi, matches[n].distance = (unsigned)b;
+      n++;
+    }
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------
  * LBP cascade, grayskull.h:769-835.  The 9 box sums of gs_lbp_code (36 loads) are taken from
  * a 4x4 lattice of integral-image corners (16 loads), corner(-1,.) = corner(.,-1) = 0.
  * ---------------------------------------------------------------------------------------- */

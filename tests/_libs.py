@@ -35,6 +35,7 @@ class Cascade(C.Structure):
     ]
 
 
+MATCH_DTYPE = np.dtype([("idx1", "<u4"), ("idx2", "<u4"), ("distance", "<u4")])
 KP_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("response", "<u4"), ("angle", "<f4"),
                      ("descriptor", "<u4", (8,))])
 RECT_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("w", "<u4"), ("h", "<u4")])
@@ -75,6 +76,8 @@ def oracle():
         lib.gso_sinf.argtypes = [C.c_float]
         lib.gso_atan2f.restype = C.c_float
         lib.gso_atan2f.argtypes = [C.c_float, C.c_float]
+        lib.gso_match_orb.restype = C.c_uint
+        lib.gso_match_orb.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_float]
         lib.gso_lbp_window.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int,
                                        C.c_float]
         lib.gso_lbp_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,
@@ -117,6 +120,8 @@ def ref():
         lib.gs_lbp_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,
                                       C.c_uint, C.c_float, C.c_float, C.c_float, C.c_int]
         lib.gs_lbp_detect.restype = C.c_uint
+        lib.gs_match_orb.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_float]
+        lib.gs_match_orb.restype = C.c_uint
         lib.ref_frontalface.restype = C.c_void_p
         lib.ref_sort_keypoints.argtypes = [C.c_void_p, C.c_uint]
         lib.ref_sort_keypoints.restype = None
@@ -179,3 +184,20 @@ def natural_like(w, h, seed=0):
     up = np.kron(small, np.ones((8, 8), np.float32))[:h, :w]
     noise = rng.normal(0, 12, size=(h, w)).astype(np.float32)
     return np.clip(up * 0.7 + noise + 30, 0, 255).astype(np.uint8)
+
+
+def desc_sets(rng, n1, n2, dup=0.3):
+    """descriptor sets with near-duplicates and exact duplicates so ties and the ratio test trigger"""
+    k1 = np.zeros(n1, KP_DTYPE); k2 = np.zeros(n2, KP_DTYPE)
+    k2["descriptor"] = rng.integers(0, 2**32, (n2, 8), dtype=np.uint64).astype(np.uint32)
+    k1["descriptor"] = rng.integers(0, 2**32, (n1, 8), dtype=np.uint64).astype(np.uint32)
+    for i in range(n1):
+        if n2 and rng.random() < dup:
+            j = int(rng.integers(0, n2))
+            d = k2["descriptor"][j].copy()
+            for _ in range(int(rng.integers(0, 40))):
+                d[int(rng.integers(0, 8))] ^= np.uint32(1 << int(rng.integers(0, 32)))
+            k1["descriptor"][i] = d
+    if n2 > 4:                                   # exact duplicates inside set 2: best == second
+        k2["descriptor"][1] = k2["descriptor"][0]
+    return k1, k2

@@ -315,6 +315,46 @@ def test_c3_orb_1080p(G, O):
         assert got[i].tobytes() == want.tobytes(), i
 
 
+def _o_match(O, k1, k2, mm, md):
+    m = np.zeros(max(mm, 1), L.MATCH_DTYPE)
+    n = O.gso_match_orb(L.ptr(k1), len(k1), L.ptr(k2 if len(k2) else np.zeros(1, L.KP_DTYPE)), len(k2), L.ptr(m), mm, md)
+    return m[:n]
+
+
+def test_match_orb_vs_oracle(G, O):
+    """gs_match_orb (reference grayskull.h:680-699): ties, empty sets, caps, max_distance extremes"""
+    rng = np.random.default_rng(16)
+    for (n1, n2, mm, md) in ((50, 60, 300, 60.0), (300, 257, 40, 60.0), (7, 0, 10, 60.0), (120, 1, 500, 300.0),
+                             (90, 33, 500, 10.0), (64, 64, 500, 0.0), (200, 500, 500, 255.5), (1250, 1250, 2500, 60.0),
+                             (9, 700, 3, 80.0), (513, 31, 513, 64.5)):
+        k1, k2 = L.desc_sets(rng, n1, n2)
+        want = _o_match(O, k1, k2, mm, md)
+        got = G.gs_match_orb(k1, k2, mm, md)
+        assert got.tobytes() == want.tobytes(), (n1, n2, mm, md, len(got), len(want))
+    assert len(G.gs_match_orb(np.zeros(0, L.KP_DTYPE), L.desc_sets(rng, 1, 9)[1], 10, 60.0)) == 0
+
+
+def test_match_orb_batch_after_extract(G, O):
+    """frame pairs: orb_extract_batch output (device resident) fed straight into match_orb_batch"""
+    import torch
+    w, h, n, nk = 640, 480, 6, 600
+    frames = np.stack([L.natural_like(w, h, 40 + (f // 2)) for f in range(n)])
+    frames[1::2] = np.roll(frames[1::2], (3, 5), axis=(1, 2))           # odd frames: shifted copies of the even ones
+    d = dev(frames)
+    _, kps, counts = G.orb_extract_batch(d, nk, 20)
+    a, b = kps[0::2].contiguous(), kps[1::2].contiguous()
+    ca, cb = counts[0::2].contiguous(), counts[1::2].contiguous()
+    m, mc = G.match_orb_batch(a, ca, b, cb, nk, 60.0)
+    torch.cuda.synchronize()
+    m = m.cpu().numpy(); mc = mc.cpu().numpy()
+    ka, kb = G.kps_to_numpy(a, ca), G.kps_to_numpy(b, cb)
+    for p in range(n // 2):
+        want = _o_match(O, ka[p], kb[p], nk, 60.0)
+        got = np.ascontiguousarray(m[p, :mc[p]]).view(np.uint32).reshape(-1, 3)
+        assert mc[p] == len(want) and got.tobytes() == want.tobytes(), p
+        assert len(want) > 20                                            # the shifted copy really matches
+
+
 def test_c4_integral_lbp_2160p(G, O, cas):
     """config C4 shape (3840x2160, sf 1.1, scales 1..4, step 2): window count, integral checksum,
     and full rect-list parity on one frame (the oracle needs a few seconds for it)"""

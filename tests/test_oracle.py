@@ -212,6 +212,18 @@ def test_diff_lbp():
             assert R.gs_lbp_window(ref_c, L.ptr(ii), w, h, x, y, s) == O.gso_lbp_window(cas.ptr, L.ptr(ii), w, h, x, y, s)
 
 
+@needs_ref
+def test_diff_match_orb():
+    R = L.ref(); rng = np.random.default_rng(6)
+    for (n1, n2, mm, md) in ((50, 60, 300, 60.0), (300, 257, 40, 60.0), (7, 0, 10, 60.0), (0, 9, 10, 60.0), (120, 1, 500, 300.0),
+                             (90, 33, 500, 10.0), (64, 64, 500, 0.0), (200, 500, 500, 255.5)):
+        k1, k2 = L.desc_sets(rng, n1, n2)
+        mr = np.zeros(max(mm, 1), L.MATCH_DTYPE); mo = np.zeros(max(mm, 1), L.MATCH_DTYPE)
+        a = R.gs_match_orb(L.ptr(k1), n1, L.ptr(k2), n2, L.ptr(mr), mm, md)
+        b = O.gso_match_orb(L.ptr(k1), n1, L.ptr(k2), n2, L.ptr(mo), mm, md)
+        assert a == b and mr[:a].tobytes() == mo[:b].tobytes(), (n1, n2, mm, md, a, b)
+
+
 # ---------------------------------------------------------------- (c) committed golden fixtures
 def _read_pgm(path):
     with open(path, "rb") as f:
