@@ -354,6 +354,8 @@ def gpu_main(args):
         out = torch.zeros_like(src)
         half = torch.empty((n, h // 2, w // 2), dtype=torch.uint8, device=dev)
         ii = torch.empty((n, h, w), dtype=torch.int32, device=dev)
+        hist = torch.empty((n, 256), dtype=torch.int32, device=dev)
+        oth = torch.empty((n,), dtype=torch.uint8, device=dev)
         px = float(n * h * w)
         kernels = {
             "gs_sobel": (lambda: api.sobel_batch(src, out=out), 2.0 * px),
@@ -367,6 +369,9 @@ def gpu_main(args):
             "gs_downsample": (lambda: api.downsample_batch(src, out=half), 1.25 * px),
             "gs_resize_to_half": (lambda: api.resize_batch(src, w // 2, h // 2, out=half), 1.25 * px),
             "gs_integral": (lambda: api.integral_batch(src, out=ii), 5.0 * px),
+            "gs_histogram": (lambda: api.histogram_batch(src, out=hist), 1.0 * px),
+            "gs_otsu_threshold": (lambda: api.otsu_threshold_batch(src, hist=hist, out=oth), 1.0 * px),
+            "gs_threshold": (lambda: api.threshold_batch(out, 128), 2.0 * px),
         }
 
         def step():
@@ -414,19 +419,19 @@ def gpu_main(args):
     e2e = None
     if wl == "c2" and not args.no_e2e:
         ne = min(n, args.e2e_frames)
-        chunk = 16
+        chunk, nstreams = args.e2e_chunk, args.e2e_streams
         hin = torch.empty((ne, h, w), dtype=torch.uint8).pin_memory()
         hout = torch.empty((ne, h, w), dtype=torch.uint8).pin_memory()
         hin.copy_(src[:ne].cpu())
-        streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        streams = [torch.cuda.Stream(device=dev) for _ in range(nstreams)]
         dbuf = [(torch.empty((chunk, h, w), dtype=torch.uint8, device=dev), torch.empty((chunk, h, w), dtype=torch.uint8, device=dev),
-                 torch.zeros((chunk, h, w), dtype=torch.uint8, device=dev)) for _ in range(2)]
+                 torch.zeros((chunk, h, w), dtype=torch.uint8, device=dev)) for _ in range(nstreams)]
         fb = chunk * h * w
 
         def e2e_step():
             for ci, lo in enumerate(range(0, ne, chunk)):
-                st = streams[ci & 1]
-                a, b, c = dbuf[ci & 1]
+                st = streams[ci % nstreams]
+                a, b, c = dbuf[ci % nstreams]
                 sp = C.c_void_p(st.cuda_stream)
                 k = min(chunk, ne - lo)
                 g._lib.check(lib.gs_b200_memcpy_h2d(C.c_void_p(a.data_ptr()), C.c_void_p(hin[lo].data_ptr()), k * h * w, sp))
@@ -451,7 +456,7 @@ def gpu_main(args):
             dt = float(t.item())
         e2e = {"value": ne * h * w * world * ksteps / dt * scale, "unit": unit, "h2d_bytes_per_step": ne * h * w,
                "d2h_bytes_per_step": ne * h * w, "frames_per_step": ne, "steps": ksteps,
-               "path": "pinned host -> gs_b200_memcpy_h2d -> gs_b200_blur_batch -> gs_b200_sobel_batch -> gs_b200_memcpy_d2h, 16-frame chunks on 2 streams"}
+               "path": "pinned host -> gs_b200_memcpy_h2d -> gs_b200_blur_batch -> gs_b200_sobel_batch -> gs_b200_memcpy_d2h, %d-frame chunks on %d streams" % (chunk, nstreams)}
         del hin, hout, dbuf
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
@@ -511,6 +516,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
     ap.add_argument("--e2e-frames", type=int, default=64)
+    ap.add_argument("--e2e-chunk", type=int, default=16)
+    ap.add_argument("--e2e-streams", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-cores", type=int, default=0, help="cap the cores of the cpu_baseline sample (default: all)")

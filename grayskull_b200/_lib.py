@@ -57,6 +57,9 @@ SIGNATURES = {
     "gs_brief_descriptor": (None, [Image, _p]),
     "gs_orb_extract": (_u, [Image, _p, _u, _u, _p]),
     "gs_match_orb": (_u, [_p, _u, _p, _u, _p, _u, _f]),
+    "gs_histogram": (None, [Image, _p]),
+    "gs_otsu_threshold": (C.c_uint8, [Image]),
+    "gs_threshold": (None, [Image, C.c_uint8]),
     "gs_lbp_window": (_u, [_p, _p, _u, _u, _i, _i, _f]),
     "gs_lbp_detect": (_u, [_p, _p, _u, _u, _p, _u, _f, _f, _f, _i]),
     # include/grayskull_b200.h
@@ -88,6 +91,10 @@ SIGNATURES = {
     "gs_b200_fast_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_orb_extract_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_set_trig_mode": (None, [_i]),
+    "gs_b200_histogram_batch": (_i, [_p, _p, _u, _u, _u, _p]),
+    "gs_b200_otsu_threshold_batch": (_i, [_p, _p, _p, _u, _u, _u, _p]),
+    "gs_b200_threshold_batch": (_i, [_p, _u, _u, _u, _u, _p]),
+    "gs_b200_threshold_each_batch": (_i, [_p, _u, _u, _u, _p, _i, _p]),
     "gs_b200_match_orb_batch": (_i, [_p, _p, _u, _p, _p, _u, _u, _p, _p, _u, _f, _p]),
     "gs_b200_lbp_detect_batch": (_i, [_p, _p, _u, _u, _u, _p, _p, _u, _f, _f, _f, _i, _p]),
     "gs_b200_lbp_window_count": (C.c_ulonglong, [_p, _u, _u, _f, _f, _f, _i]),

@@ -79,6 +79,22 @@ def gs_orb_extract(img, nkps, threshold, scoremap_buffer):
     return kps[:n]
 
 
+def gs_histogram(img):
+    hist = np.zeros(256, np.uint32)
+    lib().gs_histogram(_img(img), _vp(hist))
+    return hist
+
+
+def gs_otsu_threshold(img):
+    return int(lib().gs_otsu_threshold(_img(img)))
+
+
+def gs_threshold(img, thresh):
+    """in place, like the reference"""
+    lib().gs_threshold(_img(img), thresh)
+    return img
+
+
 def gs_match_orb(kps1, kps2, max_matches, max_distance):
     """kps1, kps2: KP_DTYPE arrays -> MATCH_DTYPE array (reference gs_match_orb)"""
     m = np.zeros(max(max_matches, 1), MATCH_DTYPE)
@@ -206,6 +222,35 @@ def orb_extract_batch(src, nkps, threshold, scoremap=None):
     check(lib().gs_b200_orb_extract_batch(_p(src), w, h, n, _p(scoremap), _p(kps), _p(counts), nkps,
                                           threshold, _stream()), "orb_extract_batch")
     return scoremap, kps, counts
+
+
+def histogram_batch(src, out=None):
+    """(n, h, w) uint8 -> (n, 256) int32-typed storage of the unsigned counts"""
+    import torch
+    n, h, w = _chk_frames(src)
+    out = torch.empty((n, 256), dtype=torch.int32, device=src.device) if out is None else out
+    check(lib().gs_b200_histogram_batch(_p(out), _p(src), w, h, n, _stream()), "histogram_batch")
+    return out
+
+
+def otsu_threshold_batch(src, hist=None, out=None):
+    """per-frame Otsu thresholds, (n,) uint8 on the device"""
+    import torch
+    n, h, w = _chk_frames(src)
+    out = torch.empty((n,), dtype=torch.uint8, device=src.device) if out is None else out
+    check(lib().gs_b200_otsu_threshold_batch(_p(out), _p(hist) if hist is not None else None, _p(src), w, h, n,
+                                             _stream()), "otsu_threshold_batch")
+    return out
+
+
+def threshold_batch(img, thresh, offset=0):
+    """in place; thresh is an int (all frames) or a (n,) uint8 device tensor (per frame, + offset)"""
+    n, h, w = _chk_frames(img)
+    if isinstance(thresh, int):
+        check(lib().gs_b200_threshold_batch(_p(img), w, h, n, thresh, _stream()), "threshold_batch")
+    else:
+        check(lib().gs_b200_threshold_each_batch(_p(img), w, h, n, _p(thresh), offset, _stream()), "threshold_each_batch")
+    return img
 
 
 def match_orb_batch(kps1, counts1, kps2, counts2, max_matches, max_distance):

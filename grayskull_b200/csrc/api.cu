@@ -203,6 +203,35 @@ unsigned gs_orb_extract(struct gs_image img, struct gs_keypoint *kps, unsigned n
   return c;
 }
 
+void gs_histogram(struct gs_image img, unsigned hist[256]) {
+  GSB_ASSERT(gs_ok(img) && hist != NULL);  // reference :200
+  Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  Buf d = in_buf(hist, sizeof(unsigned) * 256, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_histogram_batch((unsigned *)d.dev, (const uint8_t *)s.dev, img.w, img.h, 1, 0));
+  out_buf(d);
+  finish();
+}
+
+uint8_t gs_otsu_threshold(struct gs_image img) {
+  GSB_ASSERT(gs_ok(img));  // reference :206
+  Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  uint8_t *t = static_cast<uint8_t *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!t) die("device workspace allocation", 1);
+  GS_DO(gs_b200_otsu_threshold_batch(t, nullptr, (const uint8_t *)s.dev, img.w, img.h, 1, 0));
+  uint8_t out = 0;
+  GS_CUDA(cudaMemcpyAsync(&out, t, 1, cudaMemcpyDeviceToHost, 0));
+  finish();
+  return out;
+}
+
+void gs_threshold(struct gs_image img, uint8_t thresh) {
+  GSB_ASSERT(gs_ok(img));  // reference :227
+  Buf d = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  GS_DO(gs_b200_threshold_batch((uint8_t *)d.dev, img.w, img.h, 1, thresh, 0));
+  out_buf(d);
+  finish();
+}
+
 unsigned gs_match_orb(const struct gs_keypoint *kps1, unsigned n1, const struct gs_keypoint *kps2, unsigned n2,
                       struct gs_match *matches, unsigned max_matches, float max_distance) {
   GSB_ASSERT(kps1 && kps2 && matches);  // reference :683

@@ -44,6 +44,9 @@
 #define gs_lbp_window gs_cpu_lbp_window
 #define gs_lbp_detect gs_cpu_lbp_detect
 #define gs_match_orb gs_cpu_match_orb
+#define gs_histogram gs_cpu_histogram
+#define gs_otsu_threshold gs_cpu_otsu_threshold
+#define gs_threshold gs_cpu_threshold
 #include GS_UPSTREAM_HEADER
 #undef gs_blur
 #undef gs_sobel
@@ -60,6 +63,9 @@
 #undef gs_lbp_window
 #undef gs_lbp_detect
 #undef gs_match_orb
+#undef gs_histogram
+#undef gs_otsu_threshold
+#undef gs_threshold
 
 #else
 /* ---- stand-alone mode --------------------------------------------------------------- */
@@ -141,6 +147,16 @@ static inline void gs_set(struct gs_image img, unsigned x, unsigned y, uint8_t v
   if (gs_valid(img) && x < img.w && y < img.h) img.data[y * img.w + x] = value;
 }
 
+/* popcount of the xor of two 256-bit descriptors (reference grayskull.h:671-678) */
+static inline unsigned gs_hamming_distance(const uint32_t desc1[8], const uint32_t desc2[8]) {
+  unsigned dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t v = desc1[i] ^ desc2[i];
+    for (; v; v &= v - 1) dist++;
+  }
+  return dist;
+}
+
 /* inclusive box sum over [x, x+w-1] x [y, y+h-1] of a gs_integral table (grayskull.h:754-763) */
 static inline uint32_t gs_integral_sum(const unsigned *ii, unsigned iw, unsigned x, unsigned y,
                                        unsigned w, unsigned h) {
@@ -201,6 +217,13 @@ unsigned gs_lbp_detect(const struct gs_lbp_cascade *c, const unsigned *ii, unsig
  * capped at max_matches -- grayskull.h:680-699 (first "next" item after the hot path) */
 unsigned gs_match_orb(const struct gs_keypoint *kps1, unsigned n1, const struct gs_keypoint *kps2, unsigned n2,
                       struct gs_match *matches, unsigned max_matches, float max_distance);
+
+/* 256-bin histogram of all w*h pixels -- grayskull.h:199-203 */
+void gs_histogram(struct gs_image img, unsigned hist[256]);
+/* Otsu's threshold from that histogram, the reference's fp32 evaluation order -- grayskull.h:205-224 */
+uint8_t gs_otsu_threshold(struct gs_image img);
+/* in place: pixel > thresh ? 255 : 0 -- grayskull.h:226-229 */
+void gs_threshold(struct gs_image img, uint8_t thresh);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,22 @@ int gs_b200_downsample_batch(uint8_t *dst, const uint8_t *src, unsigned sw, unsi
 int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned w, unsigned h, unsigned n,
                            gs_b200_stream s);
 
+/* ---- histogram / Otsu / global threshold ------------------------------- */
+/* gs_histogram, reference grayskull.h:199-203; hist holds n tables of 256 unsigned counts */
+int gs_b200_histogram_batch(unsigned *hist, const uint8_t *src, unsigned w, unsigned h, unsigned n,
+                            gs_b200_stream s);
+/* gs_otsu_threshold, reference grayskull.h:205-224: thresh[f] for each frame.  hist (n x 256) receives the
+ * histograms; NULL uses library workspace. */
+int gs_b200_otsu_threshold_batch(uint8_t *thresh, unsigned *hist, const uint8_t *src, unsigned w,
+                                 unsigned h, unsigned n, gs_b200_stream s);
+/* gs_threshold, reference grayskull.h:226-229, in place, one threshold for every frame */
+int gs_b200_threshold_batch(uint8_t *img, unsigned w, unsigned h, unsigned n, unsigned thresh,
+                            gs_b200_stream s);
+/* same with a device-resident per-frame threshold (uint8_t)(thresh[f] + offset), e.g. Otsu's output
+ * (+10 in the reference's document scanner, nanomagick.c:191) without a host round trip */
+int gs_b200_threshold_each_batch(uint8_t *img, unsigned w, unsigned h, unsigned n, const uint8_t *thresh,
+                                 int offset, gs_b200_stream s);
+
 /* ---- FAST / ORB ------------------------------------------------------------------------- */
 /* gs_fast, reference grayskull.h:482-534.  scoremap: n maps of w*h bytes, only the interior
  * [3,w-4]x[3,h-4] is written and the untouched ring takes part in the NMS exactly as in the

@@ -548,3 +548,60 @@ GSO_API unsigned gso_lbp_detect(const struct gs_lbp_cascade *c, const uint32_t *
   }
   return n;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) N2 -- gs_histogram / gs_otsu_threshold / gs_threshold, grayskull.h:199-228.
+ * Histogram: four interleaved partial histograms merged at the end (integer counts, order free).
+ * Otsu: the reference's fp32 loop, statement for statement -- every intermediate is a float
+ * (FLT_EVAL_METHOD 0, no contraction): sum = sum_i (float)i * (float)hist[i] accumulated in bin
+ * order; per t: wb += hist[t]; skip while wb == 0; wf = npix - wb (unsigned, npix = w*h wrapped
+ * to 32 bits like the reference's unsigned product); stop at wf == 0; sumB += t*hist[t];
+ * var = ((wb*wf)*(mB-mF))*(mB-mF); strict > keeps the first maximum.
+ * ---------------------------------------------------------------------------------------- */
+GSO_API void gso_histogram(const uint8_t *src, unsigned w, unsigned h, unsigned *hist) {
+  unsigned part[4][256];
+  memset(part, 0, sizeof(part));
+  const unsigned n = w * h;
+  unsigned i = 0;
+  for (; i + 4 <= n; i += 4) part[0][src[i]]++, part[1][src[i + 1]]++, part[2][src[i + 2]]++, part[3][src[i + 3]]++;
+  for (; i < n; i++) part[0][src[i]]++;
+  for (unsigned b = 0; b < 256; b++) hist[b] = part[0][b] + part[1][b] + part[2][b] + part[3][b];
+}
+
+GSO_API unsigned gso_otsu_from_hist(const unsigned *hist, unsigned npix) {
+  float sum = 0.0f, sum_b = 0.0f, var_max = -1.0f;
+  unsigned wb = 0, best = 0;
+  for (unsigned i = 0; i < 256; i++) {
+    const float term = (float)i * (float)hist[i];
+    sum = sum + term;
+  }
+  for (unsigned t = 0; t < 256; t++) {
+    wb += hist[t];
+    if (wb == 0) continue;
+    const unsigned wf = npix - wb;
+    if (wf == 0) break;
+    const float term = (float)t * (float)hist[t];
+    sum_b = sum_b + term;
+    const float m_b = sum_b / (float)wb;
+    const float rest = sum - sum_b;
+    const float m_f = rest / (float)wf;
+    const float diff = m_b - m_f;
+    float var = (float)wb * (float)wf;
+    var = var * diff;
+    var = var * diff;
+    if (var > var_max) var_max = var, best = t;
+  }
+  return best & 0xFFu;
+}
+
+GSO_API unsigned gso_otsu_threshold(const uint8_t *src, unsigned w, unsigned h) {
+  unsigned hist[256];
+  gso_histogram(src, w, h, hist);
+  return gso_otsu_from_hist(hist, w * h);
+}
+
+GSO_API void gso_threshold(uint8_t *img, unsigned w, unsigned h, unsigned thresh) {
+  const unsigned n = w * h;
+  const uint8_t t = (uint8_t)thresh;
+  for (unsigned i = 0; i < n; i++) img[i] = (uint8_t)(-(int)(img[i] > t)); /* 0xFF or 0x00 */
+}

@@ -77,6 +77,14 @@ def oracle():
         lib.gso_atan2f.restype = C.c_float
         lib.gso_atan2f.argtypes = [C.c_float, C.c_float]
         lib.gso_match_orb.restype = C.c_uint
+        lib.gso_histogram.restype = None
+        lib.gso_histogram.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+        lib.gso_otsu_from_hist.restype = C.c_uint
+        lib.gso_otsu_from_hist.argtypes = [C.c_void_p, C.c_uint]
+        lib.gso_otsu_threshold.restype = C.c_uint
+        lib.gso_otsu_threshold.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
+        lib.gso_threshold.restype = None
+        lib.gso_threshold.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
         lib.gso_match_orb.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_float]
         lib.gso_lbp_window.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int,
                                        C.c_float]
@@ -122,6 +130,12 @@ def ref():
         lib.gs_lbp_detect.restype = C.c_uint
         lib.gs_match_orb.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_float]
         lib.gs_match_orb.restype = C.c_uint
+        lib.gs_histogram.argtypes = [Image, C.c_void_p]
+        lib.gs_histogram.restype = None
+        lib.gs_otsu_threshold.argtypes = [Image]
+        lib.gs_otsu_threshold.restype = C.c_uint8
+        lib.gs_threshold.argtypes = [Image, C.c_uint8]
+        lib.gs_threshold.restype = None
         lib.ref_frontalface.restype = C.c_void_p
         lib.ref_sort_keypoints.argtypes = [C.c_void_p, C.c_uint]
         lib.ref_sort_keypoints.restype = None

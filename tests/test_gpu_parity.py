@@ -315,6 +315,69 @@ def test_c3_orb_1080p(G, O):
         assert got[i].tobytes() == want.tobytes(), i
 
 
+def test_reference_unit_tests_run_on_cuda_path():
+    """oracle/_ref/test_overlay is the reference's own test.c, unmodified, compiled in overlay mode against
+    libgrayskull_b200.so (oracle/Makefile): its asserts on blur / threshold / histogram / otsu / morph / sobel /
+    resize / integral / adaptive threshold now exercise the CUDA kernels through host-pointer staging."""
+    import subprocess
+    exe = os.path.join(L.ORACLE_DIR, "_ref", "test_overlay")
+    if not os.path.exists(exe):
+        pytest.skip("overlay test binary not built (needs the reference tree at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stdout[-400:], r.stderr[-400:])
+
+
+def _o_hist(O, a):
+    h = np.zeros(256, np.uint32); O.gso_histogram(L.ptr(a), a.shape[1], a.shape[0], L.ptr(h)); return h
+
+
+def test_histogram_otsu_threshold_vs_oracle(G, O):
+    """gs_histogram / gs_otsu_threshold / gs_threshold (reference grayskull.h:199-229): test.c vectors through the
+    single-image API, then bimodal / flat / two-level / noise images incl. ragged sizes (scalar path)"""
+    import test_oracle as TO
+    a = np.array([[0, 50, 100], [50, 100, 150], [100, 150, 200]], np.uint8)
+    hist = G.gs_histogram(a)
+    assert hist[0] == 1 and hist[50] == 2 and hist[100] == 3 and hist[150] == 2 and hist[200] == 1 and hist.sum() == 9
+    assert G.gs_threshold(np.array([[50, 150], [75, 200]], np.uint8), 100).tolist() == [[0, 255], [0, 255]]
+    assert G.gs_otsu_threshold(np.array([[40, 50, 60], [45, 55, 50], [190, 200, 210]], np.uint8)) == 60
+    assert G.gs_otsu_threshold(np.array([[0, 85], [170, 255]], np.uint8)) == 85
+    assert G.gs_otsu_threshold(np.full((2, 2), 128, np.uint8)) == 0
+    rng = np.random.default_rng(21)
+    for a in TO.otsu_images(rng) + [L.natural_like(1024, 1024, 5), np.zeros((512, 512), np.uint8)]:
+        h, w = a.shape
+        assert np.array_equal(G.gs_histogram(a), _o_hist(O, a)), a.shape
+        t = O.gso_otsu_threshold(L.ptr(a), w, h)
+        assert G.gs_otsu_threshold(a) == t, (a.shape, t)
+        for th in (0, 100, 255, int(t)):
+            want = a.copy(); O.gso_threshold(L.ptr(want), w, h, th)
+            assert np.array_equal(G.gs_threshold(a.copy(), th), want), (a.shape, th)
+
+
+def test_histogram_otsu_threshold_batches(G, O):
+    """device-resident batches: per-frame histograms, Otsu thresholds kept on the device and fed to the
+    per-frame threshold (+10 like nanomagick.c:191); 4096^2 frames cross the chunk boundaries"""
+    import torch
+    rng = np.random.default_rng(22)
+    for (w, h, n) in ((640, 480, 9), (1000, 37, 5), (4096, 4096, 3)):
+        frames = np.stack([np.clip(rng.normal(60 + 15 * f, 20, (h, w)) * (rng.random((h, w)) < 0.5) +
+                                   rng.normal(200 - 10 * f, 15, (h, w)) * (rng.random((h, w)) < 0.4), 0, 255).astype(np.uint8)
+                           for f in range(n)])
+        if n > 2:
+            frames[1] = 77                                   # constant frame: every lane hits one bin
+        d = dev(frames)
+        hist = G.histogram_batch(d).cpu().numpy().view(np.uint32)
+        for f in range(n):
+            assert np.array_equal(hist[f], np.bincount(frames[f].ravel(), minlength=256)), (w, h, f)
+        th = G.otsu_threshold_batch(d)
+        want_t = [O.gso_otsu_from_hist(L.ptr(np.ascontiguousarray(hist[f])), w * h) for f in range(n)]
+        assert th.cpu().numpy().tolist() == want_t
+        out = G.threshold_batch(d.clone(), th, 10).cpu().numpy()
+        for f in range(n):
+            assert np.array_equal(out[f], np.where(frames[f] > ((want_t[f] + 10) & 255), 255, 0).astype(np.uint8)), (w, h, f)
+        out = G.threshold_batch(d.clone(), 128).cpu().numpy()
+        assert np.array_equal(out, np.where(frames > 128, 255, 0).astype(np.uint8))
+
+
 def _o_match(O, k1, k2, mm, md):
     m = np.zeros(max(mm, 1), L.MATCH_DTYPE)
     n = O.gso_match_orb(L.ptr(k1), len(k1), L.ptr(k2 if len(k2) else np.zeros(1, L.KP_DTYPE)), len(k2), L.ptr(m), mm, md)

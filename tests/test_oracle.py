@@ -224,6 +224,60 @@ def test_diff_match_orb():
         assert a == b and mr[:a].tobytes() == mo[:b].tobytes(), (n1, n2, mm, md, a, b)
 
 
+def otsu_images(rng):
+    """bimodal, flat, two-level, dark-heavy, noise and near-tie images: exercises wb == 0 skips, the wf == 0
+    break and fp32 ties in varBetween"""
+    out = []
+    for (w, h) in ((3, 3), (64, 48), (257, 31), (640, 480), (1, 1), (5, 1)):
+        out.append(rng.integers(0, 256, (h, w), dtype=np.uint8))
+        a = np.where(rng.random((h, w)) < 0.3, rng.normal(60, 12, (h, w)), rng.normal(190, 20, (h, w)))
+        out.append(np.clip(a, 0, 255).astype(np.uint8))
+        out.append(np.full((h, w), int(rng.integers(0, 256)), np.uint8))
+        b = np.full((h, w), 10, np.uint8); b.flat[:: max(1, (w * h) // 7)] = 250
+        out.append(b)
+        out.append((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8))
+        out.append(rng.integers(100, 104, (h, w), dtype=np.uint8))
+    out.append(L.natural_like(1920, 1080, 3))
+    return out
+
+
+def test_testc_histogram_threshold_otsu():
+    """the literal vectors of the reference's test.c:150-196"""
+    a = np.array([[0, 50, 100], [50, 100, 150], [100, 150, 200]], np.uint8)
+    hist = np.zeros(256, np.uint32); O.gso_histogram(L.ptr(a), 3, 3, L.ptr(hist))
+    assert hist[0] == 1 and hist[50] == 2 and hist[100] == 3 and hist[150] == 2 and hist[200] == 1 and hist.sum() == 9
+    t = np.array([[50, 150], [75, 200]], np.uint8); O.gso_threshold(L.ptr(t), 2, 2, 100)
+    assert t.tolist() == [[0, 255], [0, 255]]
+    assert O.gso_otsu_threshold(L.ptr(np.array([[40, 50, 60], [45, 55, 50], [190, 200, 210]], np.uint8)), 3, 3) == 60
+    assert O.gso_otsu_threshold(L.ptr(np.array([[0, 85], [170, 255]], np.uint8)), 2, 2) == 85
+    assert O.gso_otsu_threshold(L.ptr(np.full((2, 2), 128, np.uint8)), 2, 2) == 0
+
+
+@needs_ref
+def test_diff_histogram_otsu_threshold():
+    R = L.ref(); rng = np.random.default_rng(8)
+    for a in otsu_images(rng):
+        h, w = a.shape
+        hr = np.zeros(256, np.uint32); ho = np.zeros(256, np.uint32)
+        R.gs_histogram(L.img(a), L.ptr(hr)); O.gso_histogram(L.ptr(a), w, h, L.ptr(ho))
+        assert np.array_equal(hr, ho) and np.array_equal(ho, np.bincount(a.ravel(), minlength=256))
+        tr = R.gs_otsu_threshold(L.img(a)); to = O.gso_otsu_threshold(L.ptr(a), w, h)
+        assert tr == to, (a.shape, tr, to)
+        for t in (0, 100, 255, int(to)):
+            x = a.copy(); y = a.copy()
+            R.gs_threshold(L.img(x), t); O.gso_threshold(L.ptr(y), w, h, t)
+            assert np.array_equal(x, y)
+    # synthetic histograms: fp32 rounding in the sums matters once counts are large
+    for _ in range(200):
+        hist = (rng.integers(0, 1 << int(rng.integers(1, 24)), 256) * (rng.random(256) < rng.random())).astype(np.uint32)
+        if hist.sum() == 0:
+            continue
+        img = np.repeat(np.arange(256, dtype=np.uint8), hist)[None, :]
+        if img.size > 1 << 26:
+            continue
+        assert R.gs_otsu_threshold(L.img(np.ascontiguousarray(img))) == O.gso_otsu_from_hist(L.ptr(hist), int(hist.sum()))
+
+
 # ---------------------------------------------------------------- (c) committed golden fixtures
 def _read_pgm(path):
     with open(path, "rb") as f:
