@@ -347,6 +347,27 @@ def gpu_main(args):
                "pairs_per_gpu": npairs, "l2": "descriptor sets (%.0f MB per GPU) exceed the 126 MB L2" % (2 * npairs * nd * 48 / 1e6)}
         kernels = {"gs_match_orb": (step, 2.0 * npairs * nd * 48 + 12.0 * npairs * nd)}
         launches_per_step = 2
+    elif wl == "tmatch":
+        # gs_match_template, one 32x32 template against 1920x1080 frames (compute-bound:
+        # 11 instructions per 16 squared differences)
+        n, h, w = args.batch or 16, H3, W3
+        tw = th = 32
+        noise = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device=dev)
+        src = api.blur_batch(noise, 2)
+        del noise
+        tmpl = src[0, 500:500 + th, 900:900 + tw].contiguous()
+        res = torch.empty((n, h - th + 1, w - tw + 1), dtype=torch.uint8, device=dev)
+
+        def step():
+            api.match_template_batch(src, tmpl, out=res)
+            api.find_best_match_batch(res)
+
+        units_per_step = n * (h - th + 1) * (w - tw + 1) * tw * th
+        unit, scale, metric = "Gtaps/s", 1e-9, "squared differences/s, gs_match_template 32x32 template, 1920x1080 uint8"
+        cfg = {"workload": "tmatch: gs_match_template + gs_find_best_match, 32x32 template, 1920x1080, batch %d per GPU" % n,
+               "frames_per_gpu": n, "l2": "compute-bound; frames (%.0f MB per GPU) stream through L2" % (n * h * w / 1e6)}
+        kernels = {"gs_match_template": (lambda: api.match_template_batch(src, tmpl, out=res), 2.0 * n * h * w)}
+        launches_per_step = 3
     elif wl == "ops":
         # per-op table (every stencil / resampling op of the path at 4096x4096), not a driver line
         n, h, w = args.batch or 64, H2, W2
@@ -355,6 +376,9 @@ def gpu_main(args):
         half = torch.empty((n, h // 2, w // 2), dtype=torch.uint8, device=dev)
         ii = torch.empty((n, h, w), dtype=torch.int32, device=dev)
         hist = torch.empty((n, 256), dtype=torch.int32, device=dev)
+        import numpy as np
+        K_SHARPEN = np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.int8)
+        K_GAUSS = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.int8)
         oth = torch.empty((n,), dtype=torch.uint8, device=dev)
         px = float(n * h * w)
         kernels = {
@@ -369,6 +393,8 @@ def gpu_main(args):
             "gs_downsample": (lambda: api.downsample_batch(src, out=half), 1.25 * px),
             "gs_resize_to_half": (lambda: api.resize_batch(src, w // 2, h // 2, out=half), 1.25 * px),
             "gs_integral": (lambda: api.integral_batch(src, out=ii), 5.0 * px),
+            "gs_filter_sharpen": (lambda: api.filter_batch(src, K_SHARPEN, 1, out=out), 2.0 * px),
+            "gs_filter_gaussian": (lambda: api.filter_batch(src, K_GAUSS, 16, out=out), 2.0 * px),
             "gs_histogram": (lambda: api.histogram_batch(src, out=hist), 1.0 * px),
             "gs_otsu_threshold": (lambda: api.otsu_threshold_batch(src, hist=hist, out=oth), 1.0 * px),
             "gs_threshold": (lambda: api.threshold_batch(out, 128), 2.0 * px),
@@ -512,7 +538,7 @@ if __name__ == "__main__":
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "ops", "match"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5", "ops", "match", "tmatch"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU (default: the BASELINE config's batch)")
     ap.add_argument("--e2e-frames", type=int, default=64)

@@ -13,6 +13,10 @@ class Image(C.Structure):  # struct gs_image, reference grayskull.h:14-17
     _fields_ = [("w", C.c_uint), ("h", C.c_uint), ("data", C.c_void_p)]
 
 
+class Point(C.Structure):  # struct gs_point, reference grayskull.h:23-25
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint)]
+
+
 class Keypoint(C.Structure):  # struct gs_keypoint, reference grayskull.h:42-47
     _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("response", C.c_uint), ("angle", C.c_float),
                 ("descriptor", C.c_uint32 * 8)]
@@ -57,6 +61,9 @@ SIGNATURES = {
     "gs_brief_descriptor": (None, [Image, _p]),
     "gs_orb_extract": (_u, [Image, _p, _u, _u, _p]),
     "gs_match_orb": (_u, [_p, _u, _p, _u, _p, _u, _f]),
+    "gs_filter": (None, [Image, Image, Image, _u]),
+    "gs_match_template": (None, [Image, Image, Image]),
+    "gs_find_best_match": (Point, [Image]),
     "gs_histogram": (None, [Image, _p]),
     "gs_otsu_threshold": (C.c_uint8, [Image]),
     "gs_threshold": (None, [Image, C.c_uint8]),
@@ -91,6 +98,9 @@ SIGNATURES = {
     "gs_b200_fast_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_orb_extract_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_set_trig_mode": (None, [_i]),
+    "gs_b200_filter_batch": (_i, [_p, _p, _u, _u, _u, _p, _u, _u, _u, _p]),
+    "gs_b200_match_template_batch": (_i, [_p, _p, _u, _u, _u, _p, _u, _u, _p]),
+    "gs_b200_find_best_match_batch": (_i, [_p, _p, _u, _u, _u, _p]),
     "gs_b200_histogram_batch": (_i, [_p, _p, _u, _u, _u, _p]),
     "gs_b200_otsu_threshold_batch": (_i, [_p, _p, _p, _u, _u, _u, _p]),
     "gs_b200_threshold_batch": (_i, [_p, _u, _u, _u, _u, _p]),

@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import lib, check, Image, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE
+from ._lib import lib, check, Image, Point, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE
 
 
 def _img(a):
@@ -77,6 +77,24 @@ def gs_orb_extract(img, nkps, threshold, scoremap_buffer):
     kps = np.zeros(nkps, KP_DTYPE)
     n = lib().gs_orb_extract(_img(img), _vp(kps), nkps, threshold, _vp(scoremap_buffer))
     return kps[:n]
+
+
+def gs_filter(dst, src, kernel, norm):
+    """kernel: (kh, kw) int8 (or uint8 bit patterns) numpy array"""
+    k = np.ascontiguousarray(kernel).view(np.uint8)
+    lib().gs_filter(_img(dst), _img(src), _img(k), norm)
+    return dst
+
+
+def gs_match_template(img, tmpl):
+    res = np.zeros((img.shape[0] - tmpl.shape[0] + 1, img.shape[1] - tmpl.shape[1] + 1), np.uint8)
+    lib().gs_match_template(_img(img), _img(tmpl), _img(res))
+    return res
+
+
+def gs_find_best_match(result):
+    p = lib().gs_find_best_match(_img(result))
+    return p.x, p.y
 
 
 def gs_histogram(img):
@@ -222,6 +240,36 @@ def orb_extract_batch(src, nkps, threshold, scoremap=None):
     check(lib().gs_b200_orb_extract_batch(_p(src), w, h, n, _p(scoremap), _p(kps), _p(counts), nkps,
                                           threshold, _stream()), "orb_extract_batch")
     return scoremap, kps, counts
+
+
+def filter_batch(src, kernel, norm, out=None):
+    """kernel: (kh, kw) int8 numpy array (host: the weights are call parameters)"""
+    import torch
+    n, h, w = _chk_frames(src)
+    out = torch.empty_like(src) if out is None else out
+    k = np.ascontiguousarray(kernel).view(np.int8)
+    check(lib().gs_b200_filter_batch(_p(out), _p(src), w, h, n, _vp(k), k.shape[1], k.shape[0], norm, _stream()),
+          "filter_batch")
+    return out
+
+
+def match_template_batch(img, tmpl, out=None):
+    """img: (n, h, w) uint8, tmpl: (th, tw) uint8 device tensor -> (n, h-th+1, w-tw+1) uint8"""
+    import torch
+    n, h, w = _chk_frames(img)
+    th, tw = tmpl.shape
+    out = torch.empty((n, h - th + 1, w - tw + 1), dtype=torch.uint8, device=img.device) if out is None else out
+    check(lib().gs_b200_match_template_batch(_p(out), _p(img), w, h, n, _p(tmpl), tw, th, _stream()), "match_template_batch")
+    return out
+
+
+def find_best_match_batch(result):
+    """(n, rh, rw) uint8 -> (n, 2) int32 (x, y)"""
+    import torch
+    n, rh, rw = _chk_frames(result)
+    best = torch.empty((n, 2), dtype=torch.int32, device=result.device)
+    check(lib().gs_b200_find_best_match_batch(_p(best), _p(result), rw, rh, n, _stream()), "find_best_match_batch")
+    return best
 
 
 def histogram_batch(src, out=None):

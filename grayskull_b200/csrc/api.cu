@@ -203,6 +203,54 @@ unsigned gs_orb_extract(struct gs_image img, struct gs_keypoint *kps, unsigned n
   return c;
 }
 
+void gs_filter(struct gs_image dst, struct gs_image src, struct gs_image kernel, unsigned norm) {
+  GSB_ASSERT(gs_ok(src) && gs_ok(dst) && dst.w == src.w && dst.h == src.h && norm > 0);  // reference :257
+  const size_t n = (size_t)src.w * src.h;
+  // the weights are call parameters: fetch them to the host if the kernel image lives on the device
+  int8_t small[64], *kw_host = small;
+  const size_t kn = gs_ok(kernel) ? (size_t)kernel.w * kernel.h : 0;
+  if (kn > sizeof(small)) kw_host = static_cast<int8_t *>(malloc(kn));
+  if (kn && !kw_host) die("host allocation", 1);
+  if (kn) {
+    if (on_device(kernel.data)) {
+      GS_CUDA(cudaMemcpy(kw_host, kernel.data, kn, cudaMemcpyDeviceToHost));
+    } else {
+      memcpy(kw_host, kernel.data, kn);
+    }
+  }
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_filter_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, kn ? kw_host : nullptr,
+                             kn ? kernel.w : 0, kn ? kernel.h : 0, norm, 0));
+  out_buf(d);
+  finish();
+  if (kw_host != small) free(kw_host);
+}
+
+void gs_match_template(struct gs_image img, struct gs_image tmpl, struct gs_image result) {
+  GSB_ASSERT(gs_ok(img) && gs_ok(tmpl) && gs_ok(result));                                   // reference :706
+  GSB_ASSERT(img.w >= tmpl.w && img.h >= tmpl.h);                                            // reference :707
+  GSB_ASSERT(result.w == img.w - tmpl.w + 1 && result.h == img.h - tmpl.h + 1);              // reference :708
+  Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
+  Buf t = in_buf(tmpl.data, (size_t)tmpl.w * tmpl.h, gsb::WS_STAGE_B);
+  Buf r = in_buf(result.data, (size_t)result.w * result.h, gsb::WS_STAGE_C, false);
+  GS_DO(gs_b200_match_template_batch((uint8_t *)r.dev, (const uint8_t *)s.dev, img.w, img.h, 1, (const uint8_t *)t.dev,
+                                     tmpl.w, tmpl.h, 0));
+  out_buf(r);
+  finish();
+}
+
+struct gs_point gs_find_best_match(struct gs_image result) {
+  GSB_ASSERT(gs_ok(result));  // reference :727
+  Buf r = in_buf(result.data, (size_t)result.w * result.h, gsb::WS_STAGE_A);
+  struct gs_point *p = static_cast<struct gs_point *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  if (!p) die("device workspace allocation", 1);
+  GS_DO(gs_b200_find_best_match_batch(p, (const uint8_t *)r.dev, result.w, result.h, 1, 0));
+  struct gs_point out = {0, 0};
+  GS_CUDA(cudaMemcpyAsync(&out, p, sizeof(out), cudaMemcpyDeviceToHost, 0));
+  finish();
+  return out;
+}
+
 void gs_histogram(struct gs_image img, unsigned hist[256]) {
   GSB_ASSERT(gs_ok(img) && hist != NULL);  // reference :200
   Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);

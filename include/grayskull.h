@@ -47,6 +47,9 @@
 #define gs_histogram gs_cpu_histogram
 #define gs_otsu_threshold gs_cpu_otsu_threshold
 #define gs_threshold gs_cpu_threshold
+#define gs_filter gs_cpu_filter
+#define gs_match_template gs_cpu_match_template
+#define gs_find_best_match gs_cpu_find_best_match
 #include GS_UPSTREAM_HEADER
 #undef gs_blur
 #undef gs_sobel
@@ -66,6 +69,9 @@
 #undef gs_histogram
 #undef gs_otsu_threshold
 #undef gs_threshold
+#undef gs_filter
+#undef gs_match_template
+#undef gs_find_best_match
 
 #else
 /* ---- stand-alone mode --------------------------------------------------------------- */
@@ -147,6 +153,13 @@ static inline void gs_set(struct gs_image img, unsigned x, unsigned y, uint8_t v
   if (gs_valid(img) && x < img.w && y < img.h) img.data[y * img.w + x] = value;
 }
 
+/* preset 3x3 kernels for gs_filter: int8 weights stored in a gs_image, with the norm to pass alongside
+ * (reference grayskull.h:249-253) */
+#define gs_sharpen ((struct gs_image){3, 3, (uint8_t[]){0, -1, 0, -1, 5, -1, 0, -1, 0}})        /* norm 1 */
+#define gs_emboss ((struct gs_image){3, 3, (uint8_t[]){-2, -1, 0, -1, 1, 1, 0, 1, 2}})          /* norm 1 */
+#define gs_blur_box ((struct gs_image){3, 3, (uint8_t[]){1, 1, 1, 1, 1, 1, 1, 1, 1}})           /* norm 9 */
+#define gs_blur_gaussian ((struct gs_image){3, 3, (uint8_t[]){1, 2, 1, 2, 4, 2, 1, 2, 1}})      /* norm 16 */
+
 /* popcount of the xor of two 256-bit descriptors (reference grayskull.h:671-678) */
 static inline unsigned gs_hamming_distance(const uint32_t desc1[8], const uint32_t desc2[8]) {
   unsigned dist = 0;
@@ -224,6 +237,14 @@ void gs_histogram(struct gs_image img, unsigned hist[256]);
 uint8_t gs_otsu_threshold(struct gs_image img);
 /* in place: pixel > thresh ? 255 : 0 -- grayskull.h:226-229 */
 void gs_threshold(struct gs_image img, uint8_t thresh);
+
+/* kw x kh int8 convolution with zero padding, (unsigned)sum / norm clamped to 0..255 -- grayskull.h:255-266
+ *  */
+void gs_filter(struct gs_image dst, struct gs_image src, struct gs_image kernel, unsigned norm);
+/* dense sum of squared differences, 255 - min(255, ssd*255 / (tw*th*255^2)) -- grayskull.h:705-723 */
+void gs_match_template(struct gs_image img, struct gs_image tmpl, struct gs_image result);
+/* first strict maximum in raster order -- grayskull.h:725-738 */
+struct gs_point gs_find_best_match(struct gs_image result);
 
 #ifdef __cplusplus
 }

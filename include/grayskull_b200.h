@@ -99,6 +99,20 @@ int gs_b200_threshold_batch(uint8_t *img, unsigned w, unsigned h, unsigned n, un
 int gs_b200_threshold_each_batch(uint8_t *img, unsigned w, unsigned h, unsigned n, const uint8_t *thresh,
                                  int offset, gs_b200_stream s);
 
+/* ---- generic convolution / template matching --------------------------- */
+/* gs_filter, reference grayskull.h:255-266.  kernel: kw*kh int8 weights in HOST memory (row major; they are
+ * call parameters, not image data); NULL or a zero size behaves like the reference's invalid kernel image
+ * (every sum is 0). */
+int gs_b200_filter_batch(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, unsigned n,
+                         const int8_t *kernel, unsigned kw, unsigned kh, unsigned norm, gs_b200_stream s);
+/* gs_match_template, reference grayskull.h:705-723: one device-resident tw x th template against n frames;
+ * result holds n maps of (w-tw+1) x (h-th+1) bytes */
+int gs_b200_match_template_batch(uint8_t *result, const uint8_t *img, unsigned w, unsigned h, unsigned n,
+                                 const uint8_t *tmpl, unsigned tw, unsigned th, gs_b200_stream s);
+/* gs_find_best_match, reference grayskull.h:725-738, per result map */
+int gs_b200_find_best_match_batch(struct gs_point *best, const uint8_t *result, unsigned rw, unsigned rh,
+                                  unsigned n, gs_b200_stream s);
+
 /* ---- FAST / ORB ------------------------------------------------------------------------- */
 /* gs_fast, reference grayskull.h:482-534.  scoremap: n maps of w*h bytes, only the interior
  * [3,w-4]x[3,h-4] is written and the untouched ring takes part in the NMS exactly as in the

@@ -605,3 +605,61 @@ GSO_API void gso_threshold(uint8_t *img, unsigned w, unsigned h, unsigned thresh
   const uint8_t t = (uint8_t)thresh;
   for (unsigned i = 0; i < n; i++) img[i] = (uint8_t)(-(int)(img[i] > t)); /* 0xFF or 0x00 */
 }
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) N3 -- gs_filter (grayskull.h:255-266), gs_match_template / gs_find_best_match
+ * (grayskull.h:705-738).
+ * gs_filter: zero padding through gs_get, taps at (x + i - kw/2, y + j - kh/2), weights read as
+ * int8.  `sum = sum / norm` divides an int by an unsigned: the int is converted to unsigned first,
+ * the 32-bit quotient goes back into the int, then the clamp -- so a negative sum gives 0 for norm 1
+ * and (for any sane norm) 255 otherwise.  Restated with signed coordinates and explicit casts.
+ * gs_match_template: sum of squared differences in 64 bits, score = sum*255 / (tw*th*255^2),
+ * result = 255 - min(score, 255).  Restated as sum(I^2) - 2 sum(I*T) + sum(T^2) (exact in integers).
+ * ---------------------------------------------------------------------------------------- */
+GSO_API void gso_filter(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, const uint8_t *kernel, unsigned kw,
+                        unsigned kh, unsigned norm) {
+  const long ox = (long)(kw / 2), oy = (long)(kh / 2);
+  for (long y = 0; y < (long)h; y++)
+    for (long x = 0; x < (long)w; x++) {
+      int32_t sum = 0;
+      for (long j = 0; j < (long)kh; j++) {
+        const long sy = y + j - oy;
+        if (sy < 0 || sy >= (long)h) continue;
+        for (long i = 0; i < (long)kw; i++) {
+          const long sx = x + i - ox;
+          if (sx < 0 || sx >= (long)w) continue;
+          sum += (int32_t)src[sy * w + sx] * (int32_t)(int8_t)kernel[j * kw + i];
+        }
+      }
+      const uint32_t q = (uint32_t)sum / norm;
+      const int32_t v = (int32_t)q;
+      dst[y * w + x] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+GSO_API void gso_match_template(const uint8_t *img, unsigned w, unsigned h, const uint8_t *tmpl, unsigned tw, unsigned th,
+                                uint8_t *result) {
+  const unsigned rw = w - tw + 1, rh = h - th + 1;
+  uint64_t tt = 0;
+  for (unsigned k = 0; k < tw * th; k++) tt += (uint64_t)tmpl[k] * tmpl[k];
+  const uint64_t max_diff = (uint64_t)tw * th * 255u * 255u;
+  for (unsigned ry = 0; ry < rh; ry++)
+    for (unsigned rx = 0; rx < rw; rx++) {
+      uint64_t ii = 0, it = 0;
+      for (unsigned ty = 0; ty < th; ty++) {
+        const uint8_t *p = img + (size_t)(ry + ty) * w + rx, *q = tmpl + (size_t)ty * tw;
+        for (unsigned tx = 0; tx < tw; tx++) ii += (uint64_t)p[tx] * p[tx], it += (uint64_t)p[tx] * q[tx];
+      }
+      const uint64_t ssd = ii + tt - 2 * it;
+      const uint64_t score = ssd * 255u / max_diff;
+      result[(size_t)ry * rw + rx] = (uint8_t)(255u - (unsigned)(score < 255u ? score : 255u));
+    }
+}
+
+/* first strict maximum in raster order (none above 0 -> (0, 0)); returns y * w + x */
+GSO_API unsigned gso_find_best_match(const uint8_t *result, unsigned w, unsigned h) {
+  unsigned best = 0, best_score = 0;
+  for (unsigned k = 0; k < w * h; k++)
+    if (result[k] > best_score) best_score = result[k], best = k;
+  return best;
+}

@@ -19,6 +19,10 @@ class Keypoint(C.Structure):
                 ("descriptor", C.c_uint32 * 8)]
 
 
+class Point(C.Structure):
+    _fields_ = [("x", C.c_uint), ("y", C.c_uint)]
+
+
 class Rect(C.Structure):
     _fields_ = [("x", C.c_uint), ("y", C.c_uint), ("w", C.c_uint), ("h", C.c_uint)]
 
@@ -77,6 +81,12 @@ def oracle():
         lib.gso_atan2f.restype = C.c_float
         lib.gso_atan2f.argtypes = [C.c_float, C.c_float]
         lib.gso_match_orb.restype = C.c_uint
+        lib.gso_filter.restype = None
+        lib.gso_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
+        lib.gso_match_template.restype = None
+        lib.gso_match_template.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+        lib.gso_find_best_match.restype = C.c_uint
+        lib.gso_find_best_match.argtypes = [C.c_void_p, C.c_uint, C.c_uint]
         lib.gso_histogram.restype = None
         lib.gso_histogram.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
         lib.gso_otsu_from_hist.restype = C.c_uint
@@ -130,6 +140,12 @@ def ref():
         lib.gs_lbp_detect.restype = C.c_uint
         lib.gs_match_orb.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_float]
         lib.gs_match_orb.restype = C.c_uint
+        lib.gs_filter.argtypes = [Image, Image, Image, C.c_uint]
+        lib.gs_filter.restype = None
+        lib.gs_match_template.argtypes = [Image, Image, Image]
+        lib.gs_match_template.restype = None
+        lib.gs_find_best_match.argtypes = [Image]
+        lib.gs_find_best_match.restype = Point
         lib.gs_histogram.argtypes = [Image, C.c_void_p]
         lib.gs_histogram.restype = None
         lib.gs_otsu_threshold.argtypes = [Image]
@@ -215,3 +231,24 @@ def desc_sets(rng, n1, n2, dup=0.3):
     if n2 > 4:                                   # exact duplicates inside set 2: best == second
         k2["descriptor"][1] = k2["descriptor"][0]
     return k1, k2
+
+
+FILTER_KERNELS = {   # (weights as int8 rows, norm): the reference's presets (grayskull.h:249-253) and stress cases
+    "sharpen": ([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], 1),
+    "emboss": ([[-2, -1, 0], [-1, 1, 1], [0, 1, 2]], 1),
+    "box": ([[1, 1, 1], [1, 1, 1], [1, 1, 1]], 9),
+    "gaussian": ([[1, 2, 1], [2, 4, 2], [1, 2, 1]], 16),
+    "emboss_norm3": ([[-2, -1, 0], [-1, 1, 1], [0, 1, 2]], 3),       # negative sums with norm > 1 -> 255
+    "extreme": ([[127, -128, 127], [-128, 127, -128], [127, -128, 127]], 7),
+    "huge_norm": ([[1, 1, 1], [1, 1, 1], [1, 1, 1]], 3000000000),     # norm above 2^31
+    "big_norm_neg": ([[-1, 0, 0], [0, 0, 0], [0, 0, 0]], 20000000),   # (2^32 - s) / norm below 255
+    "k5": ([[1, 4, 6, 4, 1], [4, 16, 24, 16, 4], [6, 24, 36, 24, 6], [4, 16, 24, 16, 4], [1, 4, 6, 4, 1]], 256),
+    "k2x4": ([[1, -2, 3, -4], [5, 6, -7, 8]], 5),                     # even sizes: taps at -kw/2 .. kw-1-kw/2
+    "k1x1": ([[3]], 2),
+    "k7x3": ([[1, 0, -1, 2, -1, 0, 1], [2, 0, -2, 4, -2, 0, 2], [1, 0, -1, 2, -1, 0, 1]], 4),
+}
+
+
+def filter_kernel(name):
+    rows, norm = FILTER_KERNELS[name]
+    return np.ascontiguousarray(np.array(rows, np.int8).view(np.uint8)), norm

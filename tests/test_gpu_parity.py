@@ -318,7 +318,7 @@ def test_c3_orb_1080p(G, O):
 def test_reference_unit_tests_run_on_cuda_path():
     """oracle/_ref/test_overlay is the reference's own test.c, unmodified, compiled in overlay mode against
     libgrayskull_b200.so (oracle/Makefile): its asserts on blur / threshold / histogram / otsu / morph / sobel /
-    resize / integral / adaptive threshold now exercise the CUDA kernels through host-pointer staging."""
+    resize / integral / adaptive threshold / template matching now exercise the CUDA kernels through host-pointer staging."""
     import subprocess
     exe = os.path.join(L.ORACLE_DIR, "_ref", "test_overlay")
     if not os.path.exists(exe):
@@ -376,6 +376,67 @@ def test_histogram_otsu_threshold_batches(G, O):
             assert np.array_equal(out[f], np.where(frames[f] > ((want_t[f] + 10) & 255), 255, 0).astype(np.uint8)), (w, h, f)
         out = G.threshold_batch(d.clone(), 128).cpu().numpy()
         assert np.array_equal(out, np.where(frames > 128, 255, 0).astype(np.uint8))
+
+
+def test_filter_vs_oracle(G, O):
+    """gs_filter (reference grayskull.h:255-266): presets and stress kernels (negative sums with norm > 1, norms
+    beyond the magic-multiplier range, even / non-square sizes), widths on and off the 8-px fast path"""
+    rng = np.random.default_rng(31)
+    for (w, h) in ((64, 48), (640, 480), (8, 1), (33, 17), (1, 1), (250, 40)):
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8) if w < 600 else L.natural_like(w, h, 2)
+        for name in L.FILTER_KERNELS:
+            k, norm = L.filter_kernel(name)
+            want = np.zeros_like(a)
+            O.gso_filter(L.ptr(want), L.ptr(a), w, h, L.ptr(k), k.shape[1], k.shape[0], norm)
+            got = G.gs_filter(np.full_like(a, 7), a, k, norm)
+            assert np.array_equal(got, want), (w, h, name)
+    # device-resident batch, band boundaries (h not a multiple of the 16-row bands)
+    frames = np.stack([L.natural_like(256, 100, 50 + f) for f in range(5)])
+    for name in ("sharpen", "emboss", "box", "gaussian", "emboss_norm3", "k5"):
+        k, norm = L.filter_kernel(name)
+        got = G.filter_batch(dev(frames), k.view(np.int8), norm).cpu().numpy()
+        for f in range(5):
+            want = np.zeros_like(frames[f])
+            O.gso_filter(L.ptr(want), L.ptr(frames[f]), 256, 100, L.ptr(k), k.shape[1], k.shape[0], norm)
+            assert np.array_equal(got[f], want), (name, f)
+
+
+def test_match_template_vs_oracle(G, O):
+    """gs_match_template / gs_find_best_match (reference grayskull.h:705-738): test.c vectors, ragged template
+    widths (tail mask), template == image, word-aligned and unaligned image widths"""
+    import torch
+    img = np.array([[0, 0, 0, 0, 0], [0, 100, 150, 200, 0], [0, 125, 175, 225, 0], [0, 110, 160, 210, 0], [0, 0, 0, 0, 0]], np.uint8)
+    res = G.gs_match_template(img, np.ascontiguousarray(img[1:4, 1:4]))
+    assert G.gs_find_best_match(res) == (1, 1) and res[1, 1] == 255
+    s = np.full((4, 4), 50, np.uint8); s[1:3, 1:3] = 255
+    assert G.gs_find_best_match(G.gs_match_template(s, np.full((2, 2), 255, np.uint8))) == (1, 1)
+    assert G.gs_find_best_match(np.zeros((3, 4), np.uint8)) == (0, 0)
+    rng = np.random.default_rng(32)
+    for (w, h, tw, th) in ((64, 48, 8, 8), (37, 29, 37, 29), (52, 40, 1, 1), (92, 31, 17, 5), (36, 70, 4, 33), (320, 240, 31, 27),
+                           (33, 70, 6, 9), (320, 200, 320, 3)):
+        a = L.natural_like(w, h, w + h)
+        y0, x0 = int(rng.integers(0, h - th + 1)), int(rng.integers(0, w - tw + 1))
+        t = np.clip(a[y0:y0 + th, x0:x0 + tw].astype(np.int16) + rng.integers(-3, 4, (th, tw)), 0, 255).astype(np.uint8)
+        for tmpl in (t, rng.integers(0, 256, (th, tw), dtype=np.uint8)):
+            want = np.zeros((h - th + 1, w - tw + 1), np.uint8)
+            O.gso_match_template(L.ptr(a), w, h, L.ptr(tmpl), tw, th, L.ptr(want))
+            got = G.gs_match_template(a, np.ascontiguousarray(tmpl))
+            assert np.array_equal(got, want), (w, h, tw, th)
+            b = O.gso_find_best_match(L.ptr(want), want.shape[1], want.shape[0])
+            assert G.gs_find_best_match(got) == (b % want.shape[1], b // want.shape[1])
+    # batch: one template against several frames, best match per frame on the device
+    frames = np.stack([L.natural_like(256, 128, 70 + f) for f in range(4)])
+    tmpl = np.ascontiguousarray(frames[2, 40:40 + 24, 100:100 + 30])
+    r = G.match_template_batch(dev(frames), dev(tmpl))
+    best = G.find_best_match_batch(r).cpu().numpy()
+    r = r.cpu().numpy()
+    for f in range(4):
+        want = np.zeros((128 - 24 + 1, 256 - 30 + 1), np.uint8)
+        O.gso_match_template(L.ptr(frames[f]), 256, 128, L.ptr(tmpl), 30, 24, L.ptr(want))
+        assert np.array_equal(r[f], want), f
+        b = O.gso_find_best_match(L.ptr(want), want.shape[1], want.shape[0])
+        assert tuple(best[f]) == (b % want.shape[1], b // want.shape[1])
+    assert tuple(best[2]) == (100, 40)
 
 
 def _o_match(O, k1, k2, mm, md):

@@ -76,7 +76,7 @@ def test_reference_callers_compile_unmodified_against_dropin_header(tmp_path):
         syms = subprocess.run(["nm", "-u", obj], capture_output=True, text=True).stdout
         # the hot path binds to the library, not to inlined CPU code
         wanted = (("gs_blur", "gs_sobel", "gs_erode", "gs_dilate", "gs_adaptive_threshold", "gs_resize", "gs_integral",
-                   "gs_histogram", "gs_otsu_threshold", "gs_threshold")
+                   "gs_histogram", "gs_otsu_threshold", "gs_threshold", "gs_match_template", "gs_find_best_match")
                   if src == "test.c" else ("gs_blur", "gs_sobel", "gs_fast", "gs_orb_extract", "gs_match_orb", "gs_lbp_detect", "gs_integral"))
         for name in wanted:
             assert re.search(r"\bU %s\b" % name, syms), (src, name)

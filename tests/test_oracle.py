@@ -278,6 +278,52 @@ def test_diff_histogram_otsu_threshold():
         assert R.gs_otsu_threshold(L.img(np.ascontiguousarray(img))) == O.gso_otsu_from_hist(L.ptr(hist), int(hist.sum()))
 
 
+def test_testc_template_matching():
+    """the literal vectors of the reference's test.c:309-349"""
+    img = np.array([[0, 0, 0, 0, 0], [0, 100, 150, 200, 0], [0, 125, 175, 225, 0], [0, 110, 160, 210, 0], [0, 0, 0, 0, 0]], np.uint8)
+    t = np.ascontiguousarray(img[1:4, 1:4])
+    res = np.zeros((3, 3), np.uint8)
+    O.gso_match_template(L.ptr(img), 5, 5, L.ptr(t), 3, 3, L.ptr(res))
+    assert O.gso_find_best_match(L.ptr(res), 3, 3) == 1 * 3 + 1 and res[1, 1] == 255
+    s = np.full((4, 4), 50, np.uint8); s[1:3, 1:3] = 255
+    res = np.zeros((3, 3), np.uint8)
+    O.gso_match_template(L.ptr(s), 4, 4, L.ptr(np.full((2, 2), 255, np.uint8)), 2, 2, L.ptr(res))
+    assert O.gso_find_best_match(L.ptr(res), 3, 3) == 4
+
+
+@needs_ref
+def test_diff_filter():
+    R = L.ref(); rng = np.random.default_rng(9)
+    for (w, h) in ((1, 1), (2, 3), (5, 4), (33, 17), (64, 48), (257, 63)):
+        a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for name in L.FILTER_KERNELS:
+            k, norm = L.filter_kernel(name)
+            dr = np.zeros_like(a); do = np.zeros_like(a)
+            R.gs_filter(L.img(dr), L.img(a), L.img(k), norm)
+            O.gso_filter(L.ptr(do), L.ptr(a), w, h, L.ptr(k), k.shape[1], k.shape[0], norm)
+            assert np.array_equal(dr, do), (w, h, name)
+
+
+@needs_ref
+def test_diff_match_template():
+    R = L.ref(); rng = np.random.default_rng(10)
+    for (w, h, tw, th) in ((5, 5, 3, 3), (4, 4, 2, 2), (64, 48, 8, 8), (37, 29, 37, 29), (50, 40, 1, 1), (90, 31, 17, 5), (33, 70, 4, 33)):
+        a = L.natural_like(w, h, w + h)
+        y0, x0 = int(rng.integers(0, h - th + 1)), int(rng.integers(0, w - tw + 1))
+        t = np.ascontiguousarray(a[y0:y0 + th, x0:x0 + tw]).copy()
+        t = np.clip(t.astype(np.int16) + rng.integers(-3, 4, t.shape), 0, 255).astype(np.uint8)
+        for tmpl in (t, rng.integers(0, 256, (th, tw), dtype=np.uint8), np.zeros((th, tw), np.uint8)):
+            rw, rh = w - tw + 1, h - th + 1
+            rr = np.zeros((rh, rw), np.uint8); ro = np.zeros((rh, rw), np.uint8)
+            R.gs_match_template(L.img(a), L.img(tmpl), L.img(rr))
+            O.gso_match_template(L.ptr(a), w, h, L.ptr(tmpl), tw, th, L.ptr(ro))
+            assert np.array_equal(rr, ro), (w, h, tw, th)
+            p = R.gs_find_best_match(L.img(rr))
+            assert O.gso_find_best_match(L.ptr(ro), rw, rh) == p.y * rw + p.x
+    z = np.zeros((3, 4), np.uint8)
+    p = R.gs_find_best_match(L.img(z)); assert (p.x, p.y) == (0, 0) and O.gso_find_best_match(L.ptr(z), 4, 3) == 0
+
+
 # ---------------------------------------------------------------- (c) committed golden fixtures
 def _read_pgm(path):
     with open(path, "rb") as f:
