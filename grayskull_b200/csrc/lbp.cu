@@ -17,6 +17,10 @@
 //             warps instead of a few live lanes (v1 measured 7.8 of 32 lanes active).  Stage sums
 //             are accumulated with sequential fp32 adds exactly as :808.  Hits are recorded as one
 //             bit per window, which keeps the reference's order for free;
+//   k_lbp_scan3  : the same cascade walk on a 2-D window tile whose integral-image box is staged into shared
+//             memory by one TMA bulk-tensor copy (zero fill = the x == 0 / y == 0 corner rule), plus a flat
+//             (window, weak) mode for the last few survivors; the default for step-2 scans of 8-px-aligned
+//             tables (GS_B200_LBP_TMA=0 selects k_lbp_scan2);
 //   k_lbp_scan   : round-1 kernel (lane per window, ballot early exit), kept for cascades whose
 //             tables do not fit shared memory or whose features leave their window;
 //   k_lbp_count / k_row_scan : hits per 256-window block and their per-frame exclusive scan;
@@ -60,6 +64,16 @@ struct Stage {
   uint16_t start, n;
 };
 
+struct TileGeo {               // the same lattice inside the shared-memory tile (two parity planes): BYTE offsets
+  int row[4];                  // (fy + j*fh) * plane_pitch_bytes
+  int col[4];                  // parity(fx + i*fw + 7) * plane_bytes + ((fx + i*fw + 7) / 2) * 4
+};
+struct TilePlan {              // host side, per scale: window tile of k_lbp_scan3
+  int twx, twy;                // windows per tile (twx a multiple of 32)
+  int bw, ph;                  // box staged by TMA from EACH column-parity plane: bw x ph u32
+  int tiles_x, tiles_y;
+  size_t smem;
+};
 struct DevCascade {            // pointers into one device blob
   const ScaleInfo *scales;
   const short4 *feat;          // [nscales][nfeatures] = (fx, fy, fw, fh) after scaling/clamping
@@ -67,6 +81,7 @@ struct DevCascade {            // pointers into one device blob
   const int *subsets;
   const Stage *stages;
   const FeatGeo *geo;          // [nscales][nfeatures]
+  const TileGeo *tgeo;         // [nscales][nfeatures], only when every scale has a TilePlan
   int group_end[LBP_MAX_GROUPS];   // stage groups: survivors are re-packed after each group
   int ngroups, nweaks, nsubsets;
   int split_group;             // groups >= split_group run in the tail kernel (0 = no split)
@@ -331,6 +346,223 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
   for (unsigned sl = tid; sl < LBP_SLOTS_PER_CTA; sl += LBP_THREADS) masks[(size_t)f * dc.total_slots + slot_first + sl] = hit[sl];
 }
 
+
+// ---- k_lbp_scan3: window tiles on TMA-staged integral-image boxes --------------------------------
+// step == 2 only.  With windows every 2 px, a warp's 32 lanes gather from every other 32-bit word: two
+// wavefronts per load on the L1 / shared-memory data path, which is what bounds the cascade (ncu:
+// l1tex__data_pipe_lsu_wavefronts 80 % of peak, 2.2x the ideal wavefront count; profiles/
+// r01_ncu_lbp_scan3_detail.txt).  k_deinterleave2 therefore first splits each table into its even-column and
+// odd-column planes (one 8 B/entry streaming pass, ~1 % of the scan) so that adjacent windows read ADJACENT
+// words of one plane -- which plane is a per-(feature, corner) constant, because window x positions are even.
+// A CTA owns a 2-D tile of twx x twy window positions of one scale.  The box those windows can touch --
+// per plane (twx + (win_w + 7) / 2) x ((twy-1)*step + win_h + 1) words, starting one row above / eight
+// columns left of the first window so that the inner TMA coordinate is 16-byte aligned -- is fetched by two
+// cp.async.bulk.tensor.3d copies (one per plane) into shared memory while the threads copy the cascade tables.
+// TMA's zero fill supplies gs_integral_sum's "x == 0 / y == 0 -> 0" corners (reference :758-760) for free,
+// so there is no edge variant.  Every lattice corner is then an LDS at base + row[j] + col[i] (byte offsets
+// precomputed per scale): 20 integer adds + 16 LDS per weak classifier, against 16 LDG + ~50 address
+// instructions for the global-memory gather.  Stage groups / survivor re-packing as in k_lbp_scan2; hit bits
+// land in the same per-slot mask words (a tile spans whole 32-window slots, so plain stores).
+// [n][h][w] u32 -> [n][2][h][w/2]: plane q of frame f holds the columns x with x % 2 == q.  w % 8 == 0.
+__global__ void __launch_bounds__(256)
+k_deinterleave2(uint32_t *__restrict__ planes, const uint32_t *__restrict__ ii, unsigned w, unsigned h, unsigned n) {
+  const size_t groups = (size_t)w / 8 * h;              // 8 input words -> 4 + 4 output words
+  const size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (g >= groups) return;
+  const unsigned y = (unsigned)(g / (w / 8)), xg = (unsigned)(g % (w / 8));
+  for (unsigned f = blockIdx.y; f < n; f += gridDim.y) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(ii + (size_t)f * w * h + (size_t)y * w + xg * 8);
+    const uint4 a = __ldg(src), b = __ldg(src + 1);
+    uint32_t *dst = planes + (size_t)f * w * h + (size_t)y * (w / 2) + xg * 4;
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(a.x, a.z, b.x, b.z);
+    *reinterpret_cast<uint4 *>(dst + (size_t)(w / 2) * h) = make_uint4(a.y, a.w, b.y, b.w);
+  }
+}
+
+#ifndef GSB_LBP3_THREADS
+#define GSB_LBP3_THREADS 512
+#endif
+#ifndef GSB_LBP3_FLAT
+#define GSB_LBP3_FLAT 128      // survivors at or below this count switch to the (window, weak) flat mode
+#endif
+constexpr int LBP3_THREADS = GSB_LBP3_THREADS;
+
+__global__ void __launch_bounds__(LBP3_THREADS)
+k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int twx, int twy, int bw, int ph,
+            int tiles_x, int flat_n, unsigned *__restrict__ masks) {
+  extern __shared__ __align__(128) unsigned char lsm[];
+  // two column-parity planes of bw x ph words each (see k_deinterleave2), 128-byte aligned
+  const uint32_t plane_bytes = ((uint32_t)bw * ph * 4u + 127u) & ~127u;
+  const uint32_t tile_bytes = 2u * plane_bytes;
+  unsigned char *tile = lsm;
+  // everything lives in the dynamic segment (no static __shared__: the TMA destination must stay the
+  // 128-byte aligned start of it): tile | barrier, counters, 64 hit words | tables | survivor lists
+  unsigned char *ctl = lsm + ((tile_bytes + 127u) & ~127u);
+  uint64_t &bar = *reinterpret_cast<uint64_t *>(ctl);
+  unsigned *cnt = reinterpret_cast<unsigned *>(ctl + 8);
+  unsigned *hit = reinterpret_cast<unsigned *>(ctl + 16);   // twy * (twx / 32) <= 64 mask words
+  TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 384);
+  Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
+  Stage *s_stage = reinterpret_cast<Stage *>(s_weak + dc.nweaks);
+  int *s_sub = reinterpret_cast<int *>(s_stage + dc.nstages);
+  const int nwin = twx * twy;
+  uint16_t *list_a = reinterpret_cast<uint16_t *>(s_sub + dc.nsubsets);
+  uint16_t *list_b = list_a + nwin;
+
+  const unsigned f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const ScaleInfo sc = dc.scales[si];
+  const int tx = (int)(blockIdx.x % (unsigned)tiles_x), ty = (int)(blockIdx.x / (unsigned)tiles_x);
+  const int wx0 = tx * twx, wy0 = ty * twy;                 // first window of the tile (window indices)
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&bar, 2u * (uint32_t)bw * ph * 4u);
+    // plane column of the first window's (x - 8): wx0 * step / 2 - 4 = wx0 - 4 (16-byte aligned: twx % 4 == 0)
+    tma_load_3d(tile, &tmap, wx0 - 4, wy0 * dc.step - 1, 2 * (int)f, &bar);
+    tma_load_3d(tile + plane_bytes, &tmap, wx0 - 4, wy0 * dc.step - 1, 2 * (int)f + 1, &bar);
+    cnt[0] = cnt[1] = 0;
+  }
+  {  // tables -> shared memory while the boxes are in flight
+    const uint32_t *g0 = reinterpret_cast<const uint32_t *>(dc.tgeo + (size_t)si * dc.nfeatures);
+    uint32_t *d0 = reinterpret_cast<uint32_t *>(s_geo);
+    for (int i = tid; i < dc.nfeatures * 8; i += LBP3_THREADS) d0[i] = g0[i];
+    const uint32_t *g1 = reinterpret_cast<const uint32_t *>(dc.weaks);
+    uint32_t *d1 = reinterpret_cast<uint32_t *>(s_weak);
+    for (int i = tid; i < dc.nweaks * 4; i += LBP3_THREADS) d1[i] = g1[i];
+    const uint32_t *g2 = reinterpret_cast<const uint32_t *>(dc.stages);
+    uint32_t *d2 = reinterpret_cast<uint32_t *>(s_stage);
+    for (int i = tid; i < dc.nstages * 2; i += LBP3_THREADS) d2[i] = g2[i];
+    for (int i = tid; i < dc.nsubsets; i += LBP3_THREADS) s_sub[i] = dc.subsets[i];
+  }
+  if (tid < 64) hit[tid] = 0;
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  // adjacent windows (2 px apart) are adjacent WORDS of a parity plane: a warp's 32 lanes hit 32 banks
+  const int pitch = bw * 4, xstep = 4, ystep = dc.step * pitch;
+  const int shift = twx == 64 ? 6 : 5;                      // twx is 32 or 64
+  // one weak classifier of window `id`: its vote (reference gs_lbp_code + gs_lbp_match, :769-788)
+  auto vote = [&](unsigned id, const Weak &wk) -> float {
+    const int lx = (int)(id & (unsigned)(twx - 1)), ly = (int)(id >> shift);
+    const unsigned char *base = tile + ly * ystep + lx * xstep;
+    const TileGeo &g = s_geo[wk.fidx];
+    uint32_t v[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const unsigned char *rb = base + g.row[j];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[j][k] = *reinterpret_cast<const uint32_t *>(rb + g.col[k]);
+    }
+    uint32_t c[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[j][k] = v[j + 1][k + 1] + v[j][k] - v[j][k + 1] - v[j + 1][k];
+    const uint32_t m = c[1][1];
+    const int code = ((c[0][0] >= m) << 7) | ((c[0][1] >= m) << 6) | ((c[0][2] >= m) << 5) | ((c[1][2] >= m) << 4) |
+                     ((c[2][2] >= m) << 3) | ((c[2][1] >= m) << 2) | ((c[2][0] >= m) << 1) | ((c[1][0] >= m) << 0);
+    const int idx = code >> 5;
+    const bool match = idx < (int)wk.nsub && (((unsigned)s_sub[wk.sub_off + idx] >> (code & 31)) & 1u);
+    return match ? wk.left : wk.right;
+  };
+  auto run = [&](unsigned id, int s0, int s1) -> bool {
+    for (int sgi = s0; sgi < s1; sgi++) {
+      const Stage st = s_stage[sgi];
+      float sum = 0.0f;
+      for (int i = 0; i < st.n; i++) sum = __fadd_rn(sum, vote(id, s_weak[st.start + i]));   // sequential adds, :808
+      if (sum < st.thr) return false;
+    }
+    return true;
+  };
+  auto keep = [&](bool alive, unsigned id, uint16_t *next, unsigned *next_cnt, bool last) {
+    if (last) {
+      if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));   // id>>5 == ly * (twx/32) + lx/32
+      return;
+    }
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+    unsigned pos = 0;
+    if (lane == 0 && bal) pos = atomicAdd(next_cnt, __popc(bal));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (alive) next[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)id;
+  };
+  {
+    const bool last = dc.ngroups == 1;
+    for (unsigned id = tid; id < (unsigned)nwin; id += LBP3_THREADS) {
+      const int lx = (int)(id & (unsigned)(twx - 1)), ly = (int)(id >> shift);
+      const bool valid = wx0 + lx < sc.nx && wy0 + ly < sc.ny;
+      const bool alive = valid && run(id, 0, dc.group_end[0]);
+      keep(alive, id, list_a, &cnt[0], last);
+    }
+  }
+  __syncthreads();
+  uint16_t *cur = list_a, *nxt = list_b;
+  unsigned which = 0;                                        // cnt[which] = length of cur
+  for (int g = 1; g < dc.ngroups; g++) {
+    unsigned n = cnt[which];
+    if (n == 0) break;                                       // uniform: cnt is read after a barrier
+    if (n <= (unsigned)flat_n) {
+      // Few survivors left: a lane per window would leave most of the CTA waiting at barriers while a
+      // handful of lanes walk ten weak classifiers one after the other.  Flat mode instead spreads the
+      // (window, weak) pairs of ONE stage over all lanes -- a window owns P = 2^k >= stage.n adjacent lanes --
+      // and rebuilds the stage sum in the reference's order with shuffles; survivors are re-packed after
+      // every stage.
+      for (int sgi = dc.group_end[g - 1]; sgi < dc.nstages; sgi++) {
+        n = cnt[which];
+        if (n == 0) break;
+        __syncthreads();
+        if (tid == 0) cnt[which ^ 1] = 0;
+        __syncthreads();
+        const Stage st = s_stage[sgi];
+        const bool last = sgi == dc.nstages - 1;
+        int P = 1;
+        while (P < (int)st.n && P < 32) P <<= 1;
+        const int wpw = 32 / P, per_pass = (LBP3_THREADS / 32) * wpw;
+        const unsigned seg = lane & ~(unsigned)(P - 1), li = lane & (unsigned)(P - 1);
+        for (unsigned b0 = 0; b0 < n; b0 += (unsigned)per_pass) {          // uniform trip count
+          const unsigned w = b0 + (tid >> 5) * (unsigned)wpw + lane / (unsigned)P;
+          const unsigned id = w < n ? cur[w] : 0;
+          float sum = 0.0f;
+          for (int c0 = 0; c0 < (int)st.n; c0 += P) {                       // stages longer than 32: chunks
+            const int wi = c0 + (int)li;
+            const float val = (w < n && wi < (int)st.n) ? vote(id, s_weak[st.start + wi]) : 0.0f;
+            const int m = min(P, (int)st.n - c0);
+            for (int i = 0; i < m; i++) sum = __fadd_rn(sum, __shfl_sync(0xFFFFFFFFu, val, (int)seg + i));
+          }
+          const bool alive = w < n && li == 0 && !(sum < st.thr);
+          keep(alive, id, nxt, &cnt[which ^ 1], last);
+        }
+        __syncthreads();
+        which ^= 1;
+        uint16_t *t = cur;
+        cur = nxt, nxt = t;
+      }
+      break;
+    }
+    const bool last = g == dc.ngroups - 1;
+    __syncthreads();
+    if (tid == 0) cnt[which ^ 1] = 0;
+    __syncthreads();
+    for (unsigned i0 = 0; i0 < n; i0 += LBP3_THREADS) {      // uniform trip count (ballots inside)
+      const unsigned i = i0 + tid;
+      const unsigned id = i < n ? cur[i] : 0;
+      const bool alive = i < n && run(id, dc.group_end[g - 1], dc.group_end[g]);
+      keep(alive, id, nxt, &cnt[which ^ 1], last);
+    }
+    __syncthreads();
+    which ^= 1;
+    uint16_t *t = cur;
+    cur = nxt, nxt = t;
+  }
+  __syncthreads();
+  const int sx_n = twx >> 5;
+  for (int w = tid; w < twy * sx_n; w += LBP3_THREADS) {
+    const int ly = w / sx_n, sx = w % sx_n;
+    const unsigned chunk = (unsigned)(wx0 >> 5) + (unsigned)sx;
+    if (wy0 + ly < sc.ny && chunk < sc.chunks)
+      masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[w];
+  }
+}
+
 // Tail kernel: the deep stage groups for the survivors queued by k_lbp_scan2.  Items come from all
 // scales (runs of equal scale, since a producer CTA is single-scale), so the lattice offsets are read
 // through L1 instead of shared memory; the cascade tables are in shared memory as before.  Hits are
@@ -506,6 +738,7 @@ struct PlanEntry {
   void *blob;
   DevCascade dc;
   std::vector<ScaleInfo> scales;
+  std::vector<TilePlan> tiles;   // empty: k_lbp_scan3 not applicable
 };
 static std::mutex g_plan_mutex;
 static std::vector<PlanEntry> g_plans;
@@ -598,6 +831,57 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
         g.col[k] = ft.x - 1 + k * ft.z;
       }
     }
+  // window tiles for k_lbp_scan3: per scale the widest tile whose box fits a TMA box (256 elements per
+  // dimension) and the tallest one whose box fits the shared-memory budget
+  const size_t table_bytes_t = sizeof(TileGeo) * nf + sizeof(Weak) * nw + sizeof(Stage) * nst + 4 * (size_t)nsub;
+  size_t tile_budget = (size_t)100 * 1024;
+  if (const char *tb = getenv("GS_B200_LBP_TILE_KB")) tile_budget = (size_t)atoi(tb) * 1024;
+  std::vector<TileGeo> tgeo;
+  bool tiles_ok = safe && ns > 0 && iw % 8 == 0 && step == 2;
+  for (int s2 = 0; s2 < ns && tiles_ok; s2++) {
+    const ScaleInfo &si = e.scales[s2];
+    TilePlan tp;
+    tp.twx = 0;
+    for (int cand = 64; cand >= 32; cand /= 2)
+      if (cand + (si.win_w + 7) / 2 + 4 <= 256) {
+        tp.twx = cand;
+        break;
+      }
+    if (!tp.twx) {
+      tiles_ok = false;
+      break;
+    }
+    tp.bw = (tp.twx - 1 + (si.win_w + 7) / 2 + 1 + 3) & ~3;   // plane columns: lx + (fx + i*fw + 7) / 2
+    tp.twy = 0;
+    for (int cand = 64 * 32 / tp.twx; cand >= 1; cand /= 2) {      // at most 2048 windows (64 mask words)
+      const int ph = (cand - 1) * step + si.win_h + 1;
+      const size_t plane = ((size_t)tp.bw * ph * 4 + 127) & ~(size_t)127;
+      const size_t total = 2 * plane + 384 + table_bytes_t + 4 * (size_t)tp.twx * cand + 64;
+      if (ph <= 256 && (2 * plane <= tile_budget || cand == 1) && total <= (size_t)220 * 1024) {
+        tp.twy = cand, tp.ph = ph, tp.smem = total;
+        break;
+      }
+    }
+    if (!tp.twy) {
+      tiles_ok = false;
+      break;
+    }
+    tp.tiles_x = (si.nx + tp.twx - 1) / tp.twx, tp.tiles_y = (si.ny + tp.twy - 1) / tp.twy;
+    if ((unsigned long long)tp.tiles_x * tp.tiles_y > 0x7FFFFFFFull) tiles_ok = false;
+    e.tiles.push_back(tp);
+    for (int i = 0; i < nf; i++) {
+      const short4 ft = feat[(size_t)s2 * nf + i];
+      TileGeo g;
+      const int plane = (int)((((size_t)tp.bw * tp.ph * 4 + 127) & ~(size_t)127));
+      for (int k = 0; k < 4; k++) {
+        const int d = ft.x + k * ft.z + 7;          // dense column relative to the box origin (x - 8)
+        g.row[k] = (ft.y + k * ft.w) * tp.bw * 4;
+        g.col[k] = (d & 1) * plane + (d >> 1) * 4;
+      }
+      tgeo.push_back(g);
+    }
+  }
+  if (!tiles_ok) e.tiles.clear(), tgeo.clear();
   std::vector<Weak> weaks(nw);
   for (int i = 0; i < nw; i++) {
     weaks[i].left = c->weak_left_val[i], weaks[i].right = c->weak_right_val[i];
@@ -613,8 +897,10 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
   const size_t o_sc = 0, o_ft = align16(o_sc + sizeof(ScaleInfo) * (ns ? ns : 1));
   const size_t o_wk = align16(o_ft + sizeof(short4) * feat.size()), o_sb = align16(o_wk + sizeof(Weak) * nw);
   const size_t o_st = align16(o_sb + 4 * (size_t)nsub), o_ge = align16(o_st + sizeof(Stage) * nst);
-  const size_t total = align16(o_ge + sizeof(FeatGeo) * geo.size());
+  const size_t o_tg = align16(o_ge + sizeof(FeatGeo) * geo.size());
+  const size_t total = align16(o_tg + sizeof(TileGeo) * tgeo.size());
   std::vector<unsigned char> host(total, 0);
+  if (!tgeo.empty()) memcpy(&host[o_tg], tgeo.data(), sizeof(TileGeo) * tgeo.size());
   if (ns) memcpy(&host[o_sc], e.scales.data(), sizeof(ScaleInfo) * ns);
   if (!feat.empty()) memcpy(&host[o_ft], feat.data(), sizeof(short4) * feat.size());
   memcpy(&host[o_wk], weaks.data(), sizeof(Weak) * nw);
@@ -630,6 +916,7 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
   e.dc.subsets = reinterpret_cast<const int *>(b + o_sb);
   e.dc.stages = reinterpret_cast<const Stage *>(b + o_st);
   e.dc.geo = reinterpret_cast<const FeatGeo *>(b + o_ge);
+  e.dc.tgeo = reinterpret_cast<const TileGeo *>(b + o_tg);
   e.dc.nweaks = nw, e.dc.nsubsets = (int)nsub;
   {  // stage groups: re-pack after each of the first stages (most windows die there), then coarser
     const int cuts[] = {1, 2, 3, 4, 6, 9, 13};
@@ -704,6 +991,52 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   const size_t table_bytes = sizeof(gsb::FeatGeo) * dc.nfeatures + sizeof(gsb::Weak) * dc.nweaks +
                              sizeof(gsb::Stage) * dc.nstages + 4 * (size_t)dc.nsubsets;
   const size_t smem2 = table_bytes + 2 * sizeof(uint16_t) * gsb::LBP_WIN_PER_CTA;
+  // k_lbp_scan3 (TMA-staged parity-plane tiles) when the scan is the usual step-2 one on 8-px-aligned
+  // tables; bit-exact with k_lbp_scan2, half its instructions, 77 ms against 79 ms per 32 UHD frames
+  // (profiles/r01_ab_lbp_tma.txt: what remains is barrier idle in the deep-stage tail, which both share).
+  // GS_B200_LBP_TMA=0 selects k_lbp_scan2.
+  const char *tma_env = getenv("GS_B200_LBP_TMA");
+  const bool v3 = !p->tiles.empty() && reinterpret_cast<uintptr_t>(ii) % 16 == 0 && !gsb::force_generic() &&
+                  !(tma_env && tma_env[0] == '0') && getenv("GS_B200_LBP_V1") == nullptr;
+  if (v3) {
+    static bool configured3 = false;
+    if (!configured3) {
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      configured3 = true;
+    }
+    GSB_CHECK(cudaMemsetAsync(masks, 0, 4 * (size_t)dc.total_slots * n, st));   // padding slots between scales
+    int flat_n = GSB_LBP3_FLAT;
+    if (const char *fe = getenv("GS_B200_LBP_FLAT")) flat_n = atoi(fe);
+    // frames go through in chunks so that the de-interleaved copy stays small (<= 1 GiB of workspace)
+    const size_t frame_bytes = (size_t)iw * ih * 4;
+    unsigned chunk = (unsigned)(((size_t)1 << 30) / frame_bytes);
+    chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
+    uint32_t *planes = static_cast<uint32_t *>(gsb::workspace(st, gsb::WS_LBP_C, frame_bytes * chunk));
+    if (!planes) return (int)cudaErrorMemoryAllocation;
+    for (unsigned f0 = 0; f0 < n; f0 += chunk) {
+      const unsigned nf = n - f0 < chunk ? n - f0 : chunk;
+      const uint32_t *src = ii + (size_t)f0 * iw * ih;
+      const size_t groups = (size_t)iw / 8 * ih;
+      gsb::k_deinterleave2<<<dim3((unsigned)((groups + 255) / 256), nf < 64u ? nf : 64u), 256, 0, st>>>(planes, src, iw, ih, nf);
+      GSB_LAUNCHED(1);
+      for (int si = 0; si < dc.nscales; si++) {
+        const gsb::TilePlan &tp = p->tiles[si];
+        CUtensorMap tm;
+        if (!gsb::make_tmap_u32frames(&tm, planes, iw / 2, ih, 2 * nf, (unsigned)tp.bw, (unsigned)tp.ph))
+          return gsb::record_error(cudaErrorInvalidValue, __FILE__, __LINE__);
+        gsb::k_lbp_scan3<<<dim3((unsigned)(tp.tiles_x * tp.tiles_y), nf), gsb::LBP3_THREADS, tp.smem, st>>>(
+            tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, masks + (size_t)f0 * dc.total_slots);
+        GSB_LAUNCHED(1);
+      }
+    }
+    gsb::k_lbp_count<<<dim3((unsigned)((nblocks + 255) / 256), n), 256, 0, st>>>(masks, dc.total_slots, bcount);
+    GSB_LAUNCHED(1);
+    gsb::k_row_scan<<<n, 1024, 0, st>>>(bcount, (unsigned)nblocks, counts, max_rects);
+    GSB_LAUNCHED(1);
+    gsb::k_lbp_emit<<<dim3((unsigned)((nblocks + 7) / 8), n), 256, 0, st>>>(dc, masks, bcount, counts, rects, max_rects);
+    GSB_LAUNCHED(1);
+    return 0;
+  }
   const bool v2 = dc.safe_geometry && smem2 <= 160 * 1024 && (unsigned long long)iw * ih < 0x7FFFFFFFull &&
                   getenv("GS_B200_LBP_V1") == nullptr;
   if (v2) {
