@@ -361,8 +361,10 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
 // TMA's zero fill supplies gs_integral_sum's "x == 0 / y == 0 -> 0" corners (reference :758-760) for free,
 // so there is no edge variant.  Every lattice corner is then an LDS at base + row[j] + col[i] (byte offsets
 // precomputed per scale): 20 integer adds + 16 LDS per weak classifier, against 16 LDG + ~50 address
-// instructions for the global-memory gather.  Stage groups / survivor re-packing as in k_lbp_scan2; hit bits
-// land in the same per-slot mask words (a tile spans whole 32-window slots, so plain stores).
+// instructions for the global-memory gather.  Stage groups / survivor re-packing as in k_lbp_scan2, but per
+// WARP (no CTA barrier between the tile load and the mask stores); hit bits land in the same per-slot mask
+// words (a tile spans whole 32-window slots, so plain stores).  History on 32 UHD frames (ms): scan2 79.0;
+// dense tile 81.7; parity planes 78.9; + CTA-wide flat tail 77.0; warp-autonomous lists + flat tail 63.7.
 // [n][h][w] u32 -> [n][2][h][w/2]: plane q of frame f holds the columns x with x % 2 == q.  w % 8 == 0.
 __global__ void __launch_bounds__(256)
 k_deinterleave2(uint32_t *__restrict__ planes, const uint32_t *__restrict__ ii, unsigned w, unsigned h, unsigned n) {
@@ -383,7 +385,7 @@ k_deinterleave2(uint32_t *__restrict__ planes, const uint32_t *__restrict__ ii, 
 #define GSB_LBP3_THREADS 512
 #endif
 #ifndef GSB_LBP3_FLAT
-#define GSB_LBP3_FLAT 128      // survivors at or below this count switch to the (window, weak) flat mode
+#define GSB_LBP3_FLAT 8        // a warp with this many survivors or fewer switches to the (window, weak) flat mode
 #endif
 constexpr int LBP3_THREADS = GSB_LBP3_THREADS;
 
@@ -399,7 +401,6 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
   // 128-byte aligned start of it): tile | barrier, counters, 64 hit words | tables | survivor lists
   unsigned char *ctl = lsm + ((tile_bytes + 127u) & ~127u);
   uint64_t &bar = *reinterpret_cast<uint64_t *>(ctl);
-  unsigned *cnt = reinterpret_cast<unsigned *>(ctl + 8);
   unsigned *hit = reinterpret_cast<unsigned *>(ctl + 16);   // twy * (twx / 32) <= 64 mask words
   TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 384);
   Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
@@ -407,7 +408,6 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
   int *s_sub = reinterpret_cast<int *>(s_stage + dc.nstages);
   const int nwin = twx * twy;
   uint16_t *list_a = reinterpret_cast<uint16_t *>(s_sub + dc.nsubsets);
-  uint16_t *list_b = list_a + nwin;
 
   const unsigned f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const ScaleInfo sc = dc.scales[si];
@@ -420,7 +420,6 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     // plane column of the first window's (x - 8): wx0 * step / 2 - 4 = wx0 - 4 (16-byte aligned: twx % 4 == 0)
     tma_load_3d(tile, &tmap, wx0 - 4, wy0 * dc.step - 1, 2 * (int)f, &bar);
     tma_load_3d(tile + plane_bytes, &tmap, wx0 - 4, wy0 * dc.step - 1, 2 * (int)f + 1, &bar);
-    cnt[0] = cnt[1] = 0;
   }
   {  // tables -> shared memory while the boxes are in flight
     const uint32_t *g0 = reinterpret_cast<const uint32_t *>(dc.tgeo + (size_t)si * dc.nfeatures);
@@ -474,82 +473,87 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     }
     return true;
   };
-  auto keep = [&](bool alive, unsigned id, uint16_t *next, unsigned *next_cnt, bool last) {
-    if (last) {
-      if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));   // id>>5 == ly * (twx/32) + lx/32
-      return;
-    }
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
-    unsigned pos = 0;
-    if (lane == 0 && bal) pos = atomicAdd(next_cnt, __popc(bal));
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    if (alive) next[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)id;
-  };
+  // From here on every warp works alone on its own 32-window slots (slot = warp, warp + nwarps, ...): its
+  // survivors are re-packed into a warp-private list with ballots -- no shared counters, no CTA barrier until
+  // the masks are written -- so a warp that is stuck in a deep stage never holds the other fifteen up.
+  constexpr int NWARPS = LBP3_THREADS / 32;
+  const unsigned warp = tid >> 5, lt = (1u << lane) - 1u;
+  const int nslots = nwin >> 5;
+  const int cap = ((nslots + NWARPS - 1) / NWARPS) * 32;
+  uint16_t *cur = list_a + warp * cap, *nxt = list_a + (NWARPS + warp) * cap;
+  unsigned n = 0;
   {
     const bool last = dc.ngroups == 1;
-    for (unsigned id = tid; id < (unsigned)nwin; id += LBP3_THREADS) {
+    for (int slot = (int)warp; slot < nslots; slot += NWARPS) {
+      const unsigned id = (unsigned)slot * 32u + lane;
       const int lx = (int)(id & (unsigned)(twx - 1)), ly = (int)(id >> shift);
       const bool valid = wx0 + lx < sc.nx && wy0 + ly < sc.ny;
       const bool alive = valid && run(id, 0, dc.group_end[0]);
-      keep(alive, id, list_a, &cnt[0], last);
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+      if (last) {
+        if (lane == 0 && bal) hit[slot] = bal;               // bit = lane = lx % 32
+      } else {
+        if (alive) cur[n + __popc(bal & lt)] = (uint16_t)id;
+        n += __popc(bal);
+      }
     }
   }
-  __syncthreads();
-  uint16_t *cur = list_a, *nxt = list_b;
-  unsigned which = 0;                                        // cnt[which] = length of cur
-  for (int g = 1; g < dc.ngroups; g++) {
-    unsigned n = cnt[which];
-    if (n == 0) break;                                       // uniform: cnt is read after a barrier
+  __syncwarp();
+  for (int g = 1; g < dc.ngroups && n; g++) {
     if (n <= (unsigned)flat_n) {
-      // Few survivors left: a lane per window would leave most of the CTA waiting at barriers while a
-      // handful of lanes walk ten weak classifiers one after the other.  Flat mode instead spreads the
-      // (window, weak) pairs of ONE stage over all lanes -- a window owns P = 2^k >= stage.n adjacent lanes --
-      // and rebuilds the stage sum in the reference's order with shuffles; survivors are re-packed after
-      // every stage.
-      for (int sgi = dc.group_end[g - 1]; sgi < dc.nstages; sgi++) {
-        n = cnt[which];
-        if (n == 0) break;
-        __syncthreads();
-        if (tid == 0) cnt[which ^ 1] = 0;
-        __syncthreads();
+      // Few survivors: spread the (window, weak) pairs of ONE stage over the lanes -- a window owns
+      // P = 2^k >= stage.n adjacent lanes -- and rebuild the stage sum in the reference's order with
+      // shuffles; re-pack after every stage.
+      for (int sgi = dc.group_end[g - 1]; sgi < dc.nstages && n; sgi++) {
         const Stage st = s_stage[sgi];
         const bool last = sgi == dc.nstages - 1;
         int P = 1;
         while (P < (int)st.n && P < 32) P <<= 1;
-        const int wpw = 32 / P, per_pass = (LBP3_THREADS / 32) * wpw;
+        const unsigned wpw = 32u / (unsigned)P;
         const unsigned seg = lane & ~(unsigned)(P - 1), li = lane & (unsigned)(P - 1);
-        for (unsigned b0 = 0; b0 < n; b0 += (unsigned)per_pass) {          // uniform trip count
-          const unsigned w = b0 + (tid >> 5) * (unsigned)wpw + lane / (unsigned)P;
+        unsigned m = 0;
+        for (unsigned b0 = 0; b0 < n; b0 += wpw) {
+          const unsigned w = b0 + lane / (unsigned)P;
           const unsigned id = w < n ? cur[w] : 0;
           float sum = 0.0f;
           for (int c0 = 0; c0 < (int)st.n; c0 += P) {                       // stages longer than 32: chunks
             const int wi = c0 + (int)li;
             const float val = (w < n && wi < (int)st.n) ? vote(id, s_weak[st.start + wi]) : 0.0f;
-            const int m = min(P, (int)st.n - c0);
-            for (int i = 0; i < m; i++) sum = __fadd_rn(sum, __shfl_sync(0xFFFFFFFFu, val, (int)seg + i));
+            const int mm = min(P, (int)st.n - c0);
+            for (int i = 0; i < mm; i++) sum = __fadd_rn(sum, __shfl_sync(0xFFFFFFFFu, val, (int)seg + i));
           }
           const bool alive = w < n && li == 0 && !(sum < st.thr);
-          keep(alive, id, nxt, &cnt[which ^ 1], last);
+          const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+          if (last) {
+            if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));
+          } else {
+            if (alive) nxt[m + __popc(bal & lt)] = (uint16_t)id;
+            m += __popc(bal);
+          }
         }
-        __syncthreads();
-        which ^= 1;
+        __syncwarp();
+        n = last ? 0 : m;
         uint16_t *t = cur;
         cur = nxt, nxt = t;
       }
       break;
     }
     const bool last = g == dc.ngroups - 1;
-    __syncthreads();
-    if (tid == 0) cnt[which ^ 1] = 0;
-    __syncthreads();
-    for (unsigned i0 = 0; i0 < n; i0 += LBP3_THREADS) {      // uniform trip count (ballots inside)
-      const unsigned i = i0 + tid;
+    unsigned m = 0;
+    for (unsigned i0 = 0; i0 < n; i0 += 32) {
+      const unsigned i = i0 + lane;
       const unsigned id = i < n ? cur[i] : 0;
       const bool alive = i < n && run(id, dc.group_end[g - 1], dc.group_end[g]);
-      keep(alive, id, nxt, &cnt[which ^ 1], last);
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
+      if (last) {
+        if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));
+      } else {
+        if (alive) nxt[m + __popc(bal & lt)] = (uint16_t)id;
+        m += __popc(bal);
+      }
     }
-    __syncthreads();
-    which ^= 1;
+    __syncwarp();
+    n = last ? 0 : m;
     uint16_t *t = cur;
     cur = nxt, nxt = t;
   }
@@ -856,7 +860,8 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
     for (int cand = 64 * 32 / tp.twx; cand >= 1; cand /= 2) {      // at most 2048 windows (64 mask words)
       const int ph = (cand - 1) * step + si.win_h + 1;
       const size_t plane = ((size_t)tp.bw * ph * 4 + 127) & ~(size_t)127;
-      const size_t total = 2 * plane + 384 + table_bytes_t + 4 * (size_t)tp.twx * cand + 64;
+      const size_t nwarps = LBP3_THREADS / 32, slots = (size_t)tp.twx * cand / 32;
+      const size_t total = 2 * plane + 384 + table_bytes_t + 4 * nwarps * ((slots + nwarps - 1) / nwarps) * 32 + 64;
       if (ph <= 256 && (2 * plane <= tile_budget || cand == 1) && total <= (size_t)220 * 1024) {
         tp.twy = cand, tp.ph = ph, tp.smem = total;
         break;
@@ -991,10 +996,9 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   const size_t table_bytes = sizeof(gsb::FeatGeo) * dc.nfeatures + sizeof(gsb::Weak) * dc.nweaks +
                              sizeof(gsb::Stage) * dc.nstages + 4 * (size_t)dc.nsubsets;
   const size_t smem2 = table_bytes + 2 * sizeof(uint16_t) * gsb::LBP_WIN_PER_CTA;
-  // k_lbp_scan3 (TMA-staged parity-plane tiles) when the scan is the usual step-2 one on 8-px-aligned
-  // tables; bit-exact with k_lbp_scan2, half its instructions, 77 ms against 79 ms per 32 UHD frames
-  // (profiles/r01_ab_lbp_tma.txt: what remains is barrier idle in the deep-stage tail, which both share).
-  // GS_B200_LBP_TMA=0 selects k_lbp_scan2.
+  // k_lbp_scan3 (TMA-staged parity-plane tiles, warp-autonomous survivor lists) when the scan is the usual
+  // step-2 one on 8-px-aligned tables; bit-exact with k_lbp_scan2, half its instructions, 63.7 ms against
+  // 79.0 ms per 32 UHD frames (profiles/r01_ab_lbp_tma.txt).  GS_B200_LBP_TMA=0 selects k_lbp_scan2.
   const char *tma_env = getenv("GS_B200_LBP_TMA");
   const bool v3 = !p->tiles.empty() && reinterpret_cast<uintptr_t>(ii) % 16 == 0 && !gsb::force_generic() &&
                   !(tma_env && tma_env[0] == '0') && getenv("GS_B200_LBP_V1") == nullptr;
