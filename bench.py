@@ -507,7 +507,7 @@ def gpu_main(args):
         out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": {"c4": "u32", "match": "u32 (xor + popc)"}.get(wl, "u8"), "data": "synthetic (uniform iid u8, torch.randint; c3/c4: gs_blur r=3 of it)", "config": cfg, "clocks": clocks,
-               "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": launches_per_step,
+               "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(launches) // max(args.steps, 1),
                "roofline": roofline, "kernels": kres, "cpu_baseline": cpu,
                "tma_path": bool(lib.gs_b200_uses_tma(w, h, src.data_ptr()))}
         print(json.dumps(out))

@@ -924,7 +924,16 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
   e.dc.tgeo = reinterpret_cast<const TileGeo *>(b + o_tg);
   e.dc.nweaks = nw, e.dc.nsubsets = (int)nsub;
   {  // stage groups: re-pack after each of the first stages (most windows die there), then coarser
-    const int cuts[] = {1, 2, 3, 4, 6, 9, 13};
+    int cuts[7] = {1, 2, 3, 4, 6, 9, 13};
+    if (const char *ce = getenv("GS_B200_LBP_CUTS")) {      // tuning hook: up to 7 ascending stage indices, "1,2,3,5"
+      int k = 0;
+      for (const char *q = ce; *q && k < 7;) {
+        cuts[k++] = atoi(q);
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+      for (; k < 7; k++) cuts[k] = 1 << 20;
+    }
     int ng = 0;
     for (int k = 0; k < 7 && ng < LBP_MAX_GROUPS - 1; k++)
       if (cuts[k] < nst) e.dc.group_end[ng++] = cuts[k];

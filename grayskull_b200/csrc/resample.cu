@@ -55,12 +55,29 @@ __device__ __forceinline__ void resize_axis(unsigned i, unsigned sdim, unsigned 
 // A thread produces 4 adjacent dst pixels for RS_ROWS rows: the x-axis coefficients (two IEEE
 // divisions per pixel in the reference's formula) are computed once per thread, the y-axis ones once
 // per row, and the 4 results leave as one 32-bit store.
+// PAIRS path: when a thread's eight taps are the eight consecutive source bytes x0[0] .. x0[0] + 7 (every
+// 2:1 reduction in x, the pyramid / "half size" case) and that address is 8-byte aligned, a source row is
+// ONE 64-bit load instead of eight byte gathers, and the u8 -> f32 conversions pick their byte straight out
+// of the loaded words.  Threads that do not qualify (other ratios, clamped edges) take the gather path.
 constexpr int RS_ROWS = 8;
+#ifndef GSB_RS_PAIRS
+#define GSB_RS_PAIRS 1
+#endif
+
+__device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c11, float omx, float dx, float omy,
+                                        float dy) {
+  float p = __fmul_rn(__fmul_rn(c00, omx), omy);                  // reference :181-184, left to right
+  p = __fadd_rn(p, __fmul_rn(__fmul_rn(c01, dx), omy));
+  p = __fadd_rn(p, __fmul_rn(__fmul_rn(c10, omx), dy));
+  p = __fadd_rn(p, __fmul_rn(__fmul_rn(c11, dx), dy));
+  return p;
+}
+__device__ __forceinline__ float byte_f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src, unsigned sw,
-         unsigned sh, unsigned n) {
+         unsigned sh, unsigned n, bool src_aligned8) {
   const unsigned x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
   const unsigned yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * RS_ROWS;
   if (x >= dw || yb >= dh) return;
@@ -71,6 +88,9 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
     resize_axis(min(x + j, dw - 1), sw, dw, x0[j], x1[j], dx[j]);
     omx[j] = __fsub_rn(1.0f, dx[j]);
   }
+  bool pairs = GSB_RS_PAIRS && VEC && src_aligned8 && x0[0] % 8 == 0 && x + 3 < dw;
+#pragma unroll
+  for (int j = 0; j < 4; j++) pairs = pairs && x0[j] == x0[0] + 2 * j && x1[j] == x0[j] + 1;
   for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
     const uint8_t *s = src + (size_t)f * sw * sh;
     uint8_t *d = dst + (size_t)f * dw * dh;
@@ -82,15 +102,21 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
       const float omy = __fsub_rn(1.0f, dy);
       const uint8_t *r0 = s + (size_t)y0 * sw, *r1 = s + (size_t)y1 * sw;
       uint32_t out = 0;
+      if (pairs) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(r0 + x0[0])), b = __ldg(reinterpret_cast<const uint2 *>(r1 + x0[0]));
+        const float p0 = bilerp(byte_f(a.x, 0), byte_f(a.x, 1), byte_f(b.x, 0), byte_f(b.x, 1), omx[0], dx[0], omy, dy);
+        const float p1 = bilerp(byte_f(a.x, 2), byte_f(a.x, 3), byte_f(b.x, 2), byte_f(b.x, 3), omx[1], dx[1], omy, dy);
+        const float p2 = bilerp(byte_f(a.y, 0), byte_f(a.y, 1), byte_f(b.y, 0), byte_f(b.y, 1), omx[2], dx[2], omy, dy);
+        const float p3 = bilerp(byte_f(a.y, 2), byte_f(a.y, 3), byte_f(b.y, 2), byte_f(b.y, 3), omx[3], dx[3], omy, dy);
+        out = (__float2uint_rz(p0) & 0xFFu) | ((__float2uint_rz(p1) & 0xFFu) << 8) | ((__float2uint_rz(p2) & 0xFFu) << 16) |
+              ((__float2uint_rz(p3) & 0xFFu) << 24);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const float c00 = (float)__ldg(r0 + x0[j]), c01 = (float)__ldg(r0 + x1[j]);
-        const float c10 = (float)__ldg(r1 + x0[j]), c11 = (float)__ldg(r1 + x1[j]);
-        float p = __fmul_rn(__fmul_rn(c00, omx[j]), omy);
-        p = __fadd_rn(p, __fmul_rn(__fmul_rn(c01, dx[j]), omy));
-        p = __fadd_rn(p, __fmul_rn(__fmul_rn(c10, omx[j]), dy));
-        p = __fadd_rn(p, __fmul_rn(__fmul_rn(c11, dx[j]), dy));
-        out |= (__float2uint_rz(p) & 0xFFu) << (8 * j);
+        for (int j = 0; j < 4; j++) {
+          const float c00 = (float)__ldg(r0 + x0[j]), c01 = (float)__ldg(r0 + x1[j]);
+          const float c10 = (float)__ldg(r1 + x0[j]), c11 = (float)__ldg(r1 + x1[j]);
+          out |= (__float2uint_rz(bilerp(c00, c01, c10, c11, omx[j], dx[j], omy, dy)) & 0xFFu) << (8 * j);
+        }
       }
       uint8_t *q = d + (size_t)y * dw + x;
       if (VEC) {
@@ -129,10 +155,11 @@ int gs_b200_resize_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *
   if (n == 0) return 0;
   dim3 grid((dw + 127) / 128, (dh + 8 * gsb::RS_ROWS - 1) / (8 * gsb::RS_ROWS), n < 65535u ? n : 65535u);
   GSB_ASSERT(grid.y <= 65535u);
+  const bool aligned8 = sw % 8 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0;   // every source row 8-byte aligned
   if (dw % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0)
-    gsb::k_resize<true><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n);
+    gsb::k_resize<true><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, aligned8);
   else
-    gsb::k_resize<false><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n);
+    gsb::k_resize<false><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, aligned8);
   GSB_LAUNCHED(1);
   return 0;
 }

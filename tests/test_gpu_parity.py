@@ -185,7 +185,8 @@ def test_stencils_vs_oracle(G, O, force_generic):
                 gd = G.downsample_batch(src).cpu().numpy()
                 for i in range(n):
                     assert np.array_equal(gd[i], o_down(O, frames[i])), ("down", w, h)
-            for (dw, dh) in ((w // 2 + 1, h // 2 + 1), (w * 2 + 3, h + 5), (w, h), (7, 3)):
+            for (dw, dh) in ((w // 2 + 1, h // 2 + 1), (w * 2 + 3, h + 5), (w, h), (7, 3), (max(w // 2, 1), max(h // 2, 1)),
+                             (max(w // 2, 1), h + 1)):
                 gr = G.resize_batch(src, dw, dh).cpu().numpy()
                 for i in range(n):
                     assert np.array_equal(gr[i], o_resize(O, frames[i], dw, dh)), ("resize", w, h, dw, dh)
