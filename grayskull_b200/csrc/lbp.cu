@@ -17,10 +17,12 @@
 //             warps instead of a few live lanes (v1 measured 7.8 of 32 lanes active).  Stage sums
 //             are accumulated with sequential fp32 adds exactly as :808.  Hits are recorded as one
 //             bit per window, which keeps the reference's order for free;
-//   k_lbp_scan3  : the same cascade walk on a 2-D window tile whose integral-image box is staged into shared
-//             memory by one TMA bulk-tensor copy (zero fill = the x == 0 / y == 0 corner rule), plus a flat
-//             (window, weak) mode for the last few survivors; the default for step-2 scans of 8-px-aligned
-//             tables (GS_B200_LBP_TMA=0 selects k_lbp_scan2);
+//   k_lbp_scan3  : the default for step-2 scans of 8-px-aligned tables (GS_B200_LBP_TMA=0 selects
+//             k_lbp_scan2): the same cascade walk on a 2-D window tile whose integral-image boxes (even- and
+//             odd-column planes made by k_deinterleave2, so that step-2 windows gather from adjacent words)
+//             are staged into shared memory by two TMA bulk-tensor copies (zero fill = the x == 0 / y == 0
+//             corner rule); each warp re-packs its own survivors (no CTA barriers) and finishes its last few
+//             in a flat (window, weak) mode;
 //   k_lbp_scan   : round-1 kernel (lane per window, ballot early exit), kept for cascades whose
 //             tables do not fit shared memory or whose features leave their window;
 //   k_lbp_count / k_row_scan : hits per 256-window block and their per-frame exclusive scan;
@@ -84,8 +86,6 @@ struct DevCascade {            // pointers into one device blob
   const TileGeo *tgeo;         // [nscales][nfeatures], only when every scale has a TilePlan
   int group_end[LBP_MAX_GROUPS];   // stage groups: survivors are re-packed after each group
   int ngroups, nweaks, nsubsets;
-  int split_group;             // groups >= split_group run in the tail kernel (0 = no split)
-  unsigned queue_cap;          // survivor queue entries per frame
   int nscales, nfeatures, nstages;
   unsigned long long total_slots, total_windows;
   int step;
@@ -208,8 +208,7 @@ __device__ __forceinline__ bool weak_match(const uint32_t *__restrict__ ii, int 
 }
 
 __global__ void __launch_bounds__(LBP_THREADS)
-k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCascade dc, unsigned *__restrict__ masks,
-            unsigned *__restrict__ queue, unsigned *__restrict__ qcount) {
+k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCascade dc, unsigned *__restrict__ masks) {
   extern __shared__ __align__(16) unsigned char lsm[];
   FeatGeo *s_geo = reinterpret_cast<FeatGeo *>(lsm);
   Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
@@ -221,7 +220,6 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
   __shared__ int slot_y[LBP_SLOTS_PER_CTA], slot_x[LBP_SLOTS_PER_CTA];   // window origin of lane 0, -1 = empty slot
   __shared__ int s_scale;
   __shared__ unsigned cnt[2];
-  __shared__ unsigned s_qbase;
 
   const unsigned f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const unsigned long long slot_first = (unsigned long long)blockIdx.x * LBP_SLOTS_PER_CTA;
@@ -307,29 +305,6 @@ k_lbp_scan2(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCa
   for (int g = 1; g < dc.ngroups; g++) {
     const unsigned n = cnt[(g - 1) & 1];
     const bool last = g == dc.ngroups - 1;
-    if (g == dc.split_group) {
-      // hand the (few) survivors to the tail kernel, which runs the deep stages with full warps
-      // gathered from every CTA; if the queue is full this CTA simply carries on by itself
-      if (n == 0) break;
-      if (tid == 0) {
-        unsigned b = atomicAdd(&qcount[f], n);
-        if (b + n > dc.queue_cap) {
-          atomicSub(&qcount[f], n);
-          b = 0xFFFFFFFFu;
-        }
-        s_qbase = b;
-      }
-      __syncthreads();
-      const unsigned qb = s_qbase;
-      if (qb != 0xFFFFFFFFu) {
-        unsigned *q = queue + (size_t)f * dc.queue_cap + qb;
-        for (unsigned i = tid; i < n; i += LBP_THREADS) {
-          const unsigned id = cur[i];
-          q[i] = (unsigned)((slot_first + (id >> 5)) * 32 + (id & 31));
-        }
-        break;
-      }
-    }
     if (tid == 0) cnt[g & 1] = 0;
     __syncthreads();
     for (unsigned i0 = 0; i0 < n; i0 += LBP_THREADS) {     // uniform trip count (ballots inside)
@@ -564,107 +539,6 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     const unsigned chunk = (unsigned)(wx0 >> 5) + (unsigned)sx;
     if (wy0 + ly < sc.ny && chunk < sc.chunks)
       masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[w];
-  }
-}
-
-// Tail kernel: the deep stage groups for the survivors queued by k_lbp_scan2.  Items come from all
-// scales (runs of equal scale, since a producer CTA is single-scale), so the lattice offsets are read
-// through L1 instead of shared memory; the cascade tables are in shared memory as before.  Hits are
-// OR-ed into the window bit masks.
-constexpr int LBT_ITEMS = 2048;
-__global__ void __launch_bounds__(256)
-k_lbp_tail(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCascade dc, unsigned *__restrict__ masks,
-           const unsigned *__restrict__ queue, const unsigned *__restrict__ qcount) {
-  extern __shared__ __align__(16) unsigned char lsm[];
-  Weak *s_weak = reinterpret_cast<Weak *>(lsm);
-  Stage *s_stage = reinterpret_cast<Stage *>(s_weak + dc.nweaks);
-  int *s_sub = reinterpret_cast<int *>(s_stage + dc.nstages);
-  int *it_base = s_sub + dc.nsubsets;                                   // [LBT_ITEMS] y * iw + x
-  unsigned *it_gid = reinterpret_cast<unsigned *>(it_base + LBT_ITEMS);  // [LBT_ITEMS] global window id
-  uint8_t *it_scale = reinterpret_cast<uint8_t *>(it_gid + LBT_ITEMS);   // [LBT_ITEMS] scale | x==0 <<6 | y==0 <<7
-  uint16_t *list_a = reinterpret_cast<uint16_t *>(it_scale + LBT_ITEMS);
-  uint16_t *list_b = list_a + LBT_ITEMS;
-  __shared__ unsigned cnt[2];
-  const unsigned f = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const unsigned qn = min(qcount[f], dc.queue_cap);
-  if ((unsigned long long)blockIdx.x * LBT_ITEMS >= qn) return;
-  const uint32_t *ii = ii_all + (size_t)f * iw * ih;
-  const unsigned *q = queue + (size_t)f * dc.queue_cap;
-  {
-    const uint32_t *g1 = reinterpret_cast<const uint32_t *>(dc.weaks);
-    uint32_t *d1 = reinterpret_cast<uint32_t *>(s_weak);
-    for (int i = tid; i < dc.nweaks * 4; i += 256) d1[i] = g1[i];
-    const uint32_t *g2 = reinterpret_cast<const uint32_t *>(dc.stages);
-    uint32_t *d2 = reinterpret_cast<uint32_t *>(s_stage);
-    for (int i = tid; i < dc.nstages * 2; i += 256) d2[i] = g2[i];
-    for (int i = tid; i < dc.nsubsets; i += 256) s_sub[i] = dc.subsets[i];
-  }
-  auto run = [&](unsigned it, int s0, int s1) -> bool {
-    const int base = it_base[it];
-    const unsigned sb = it_scale[it];
-    const bool x0 = (sb >> 6) & 1u, y0 = (sb >> 7) & 1u;
-    const FeatGeo *geo = dc.geo + (size_t)(sb & 63u) * dc.nfeatures;
-    for (int si = s0; si < s1; si++) {
-      const Stage st = s_stage[si];
-      float sum = 0.0f;
-      for (int i = 0; i < st.n; i++) {
-        const Weak wk = s_weak[st.start + i];
-        FeatGeo g;
-        const int4 r4 = __ldg(reinterpret_cast<const int4 *>(geo + wk.fidx)), c4 = __ldg(reinterpret_cast<const int4 *>(geo + wk.fidx) + 1);
-        g.row[0] = r4.x, g.row[1] = r4.y, g.row[2] = r4.z, g.row[3] = r4.w;
-        g.col[0] = c4.x, g.col[1] = c4.y, g.col[2] = c4.z, g.col[3] = c4.w;
-        const bool m = (x0 || y0) ? weak_match<true>(ii, base, x0, y0, g, wk, s_sub)
-                                  : weak_match<false>(ii, base, false, false, g, wk, s_sub);
-        sum = __fadd_rn(sum, m ? wk.left : wk.right);
-      }
-      if (sum < st.thr) return false;
-    }
-    return true;
-  };
-  for (unsigned chunk = blockIdx.x; (unsigned long long)chunk * LBT_ITEMS < qn; chunk += gridDim.x) {
-    const unsigned first = chunk * LBT_ITEMS, n0 = min((unsigned)LBT_ITEMS, qn - first);
-    __syncthreads();                                   // previous chunk's lists are no longer read
-    for (unsigned i = tid; i < n0; i += 256) {         // decode the queued window ids once
-      const unsigned gid = q[first + i];
-      const unsigned long long slot = gid >> 5;
-      int si = 0;
-      while (si + 1 < dc.nscales && slot >= dc.scales[si + 1].slot0) si++;
-      const ScaleInfo sc = dc.scales[si];
-      const unsigned long long rel = slot - sc.slot0;
-      const int y = (int)(rel / sc.chunks) * dc.step, x = ((int)(rel % sc.chunks) * 32 + (int)(gid & 31)) * dc.step;
-      it_base[i] = y * (int)iw + x;
-      it_gid[i] = gid;
-      it_scale[i] = (uint8_t)(si | ((x == 0) << 6) | ((y == 0) << 7));
-      list_a[i] = (uint16_t)i;
-    }
-    if (tid == 0) cnt[0] = n0, cnt[1] = 0;
-    __syncthreads();
-    uint16_t *cur = list_a, *nxt = list_b;
-    unsigned which = 0;
-    for (int g = dc.split_group; g < dc.ngroups; g++) {
-      const unsigned n = cnt[which];
-      const bool last = g == dc.ngroups - 1;
-      for (unsigned i0 = 0; i0 < n; i0 += 256) {       // uniform trip count (ballots inside)
-        const unsigned i = i0 + tid;
-        const unsigned it = i < n ? cur[i] : 0;
-        const bool alive = i < n && run(it, dc.group_end[g - 1], dc.group_end[g]);
-        if (last) {
-          if (alive) atomicOr(&masks[(size_t)f * dc.total_slots + (it_gid[it] >> 5)], 1u << (it_gid[it] & 31));
-        } else {
-          const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
-          unsigned pos = 0;
-          if (lane == 0 && bal) pos = atomicAdd(&cnt[which ^ 1], __popc(bal));
-          pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-          if (alive) nxt[pos + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)it;
-        }
-      }
-      __syncthreads();
-      if (tid == 0) cnt[which] = 0;
-      which ^= 1;
-      uint16_t *t = cur;
-      cur = nxt, nxt = t;
-      __syncthreads();
-    }
   }
 }
 
@@ -940,24 +814,14 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
     e.dc.group_end[ng++] = nst;
     e.dc.ngroups = ng;
     for (int k = ng; k < LBP_MAX_GROUPS; k++) e.dc.group_end[k] = nst;
-    // the first 5 groups (stages 0..5 of a 20-stage cascade) stay in the scan kernel
-    // (opt-in: measured on B200 the separate tail kernel is latency-bound -- 28 ms vs the 19 ms the deep
-    // stages cost inside the scan kernel per 32 UHD frames -- so the default keeps everything in one kernel)
-    e.dc.split_group = (ng > 5 && ns <= 64 && getenv("GS_B200_LBP_SPLIT") != nullptr) ? 5 : 0;
   }
   e.dc.nscales = ns, e.dc.nfeatures = nf, e.dc.nstages = nst, e.dc.step = step;
   e.dc.safe_geometry = safe;
   e.dc.total_slots = 0, e.dc.total_windows = 0;
-  e.dc.queue_cap = 0;
   for (auto &s : e.scales) {
     const unsigned long long end = s.slot0 + (unsigned long long)s.chunks * s.ny;
     e.dc.total_slots = (end + LBP_SLOTS_PER_CTA - 1) / LBP_SLOTS_PER_CTA * LBP_SLOTS_PER_CTA;
     e.dc.total_windows += (unsigned long long)s.nx * s.ny;
-  }
-  {
-    const unsigned long long cap = e.dc.total_windows / 16 + 4096;     // survivors of stage 5 are a few percent
-    e.dc.queue_cap = (unsigned)(cap < 0x3FFFFFFFull ? cap : 0x3FFFFFFFull);
-    if (e.dc.total_slots * 32 > 0xFFFFFFFFull) e.dc.split_group = 0;   // window ids must fit 32 bits
   }
   if (g_plans.size() >= 16) {  // tiny cache: drop the oldest
     cudaFree(g_plans.front().blob);
@@ -1059,34 +923,8 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
       configured = smem2;
     }
     dim3 grid2((unsigned)(dc.total_slots / gsb::LBP_SLOTS_PER_CTA), n);
-    unsigned *queue = nullptr, *qcount = nullptr;
-    gsb::DevCascade dcl = dc;
-    if (dc.split_group) {
-      // queue memory is bounded: fall back to the unsplit kernel for very large batches
-      const size_t qbytes = sizeof(unsigned) * ((size_t)dc.queue_cap * n + n);
-      if (qbytes <= ((size_t)6 << 30)) {
-        qcount = static_cast<unsigned *>(gsb::workspace(st, gsb::WS_LBP_C, qbytes));
-        if (!qcount) return (int)cudaErrorMemoryAllocation;
-        queue = qcount + n;
-        GSB_CHECK(cudaMemsetAsync(qcount, 0, sizeof(unsigned) * n, st));
-      } else {
-        dcl.split_group = 0;
-      }
-    }
-    gsb::k_lbp_scan2<<<grid2, gsb::LBP_THREADS, smem2, st>>>(ii, iw, ih, dcl, masks, queue, qcount);
+    gsb::k_lbp_scan2<<<grid2, gsb::LBP_THREADS, smem2, st>>>(ii, iw, ih, dc, masks);
     GSB_LAUNCHED(1);
-    if (dcl.split_group) {
-      const size_t smem_t = sizeof(gsb::Weak) * dc.nweaks + sizeof(gsb::Stage) * dc.nstages + 4 * (size_t)dc.nsubsets +
-                            (size_t)gsb::LBT_ITEMS * (4 + 4 + 1 + 2 + 2) + 16;
-      static size_t configured_t = 0;
-      if (smem_t > configured_t) {
-        GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-        configured_t = smem_t;
-      }
-      const unsigned chunks = (dc.queue_cap + gsb::LBT_ITEMS - 1) / gsb::LBT_ITEMS;
-      gsb::k_lbp_tail<<<dim3(chunks < 96u ? chunks : 96u, n), 256, smem_t, st>>>(ii, iw, ih, dcl, masks, queue, qcount);
-      GSB_LAUNCHED(1);
-    }
     gsb::k_lbp_count<<<dim3((unsigned)((nblocks + 255) / 256), n), 256, 0, st>>>(masks, dc.total_slots, bcount);
   } else if (dc.safe_geometry) {
     gsb::k_lbp_scan<false><<<grid, 256, 0, st>>>(ii, iw, ih, dc, masks, bcount);
