@@ -34,6 +34,7 @@ def nvcc():
 def _deps_mtime():
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     files += [os.path.join(os.path.dirname(HERE), "include", f) for f in ("grayskull.h", "grayskull_b200.h")]
+    files.append(os.path.join(HERE, "cli", "gsb_magick.c"))
     return max(os.path.getmtime(f) for f in files)
 
 
@@ -72,7 +73,21 @@ def build(force=False, verbose=False, defines=(), out=None):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    if not out:
+        build_cli()
     return lib_out
+
+
+def build_cli():
+    """gsb_magick: the C99 batch-pipeline CLI on the device-resident ABI (cli/gsb_magick.c)"""
+    exe = os.path.join(HERE, "gsb_magick")
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-pedantic", "-D_POSIX_C_SOURCE=200809L",
+           "-I", os.path.join(os.path.dirname(HERE), "include"), "-o", exe, os.path.join(HERE, "cli", "gsb_magick.c"),
+           "-L" + HERE, "-l:" + os.path.basename(LIB), "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gsb_magick build failed:\n" + r.stdout + r.stderr)
+    return exe
 
 
 if __name__ == "__main__":

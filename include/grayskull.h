@@ -139,6 +139,50 @@ static inline struct gs_image gs_alloc(unsigned w, unsigned h) {
   return img;
 }
 static inline void gs_free(struct gs_image img) { free(img.data); }
+
+/* Binary PGM (P5, maxval 255) I/O, "-" = stdin / stdout -- the reference's on-disk format
+ * (grayskull.h:111-136).  Header tokens may be separated by any white space; '#' comments are skipped. */
+static inline int gs__pgm_token(FILE *f, unsigned *out) {
+  int c = fgetc(f);
+  unsigned v = 0, digits = 0;
+  while (c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '#') {
+    if (c == '#')
+      while (c != '\n' && c != EOF) c = fgetc(f);
+    else
+      c = fgetc(f);
+  }
+  while (c >= '0' && c <= '9') v = v * 10u + (unsigned)(c - '0'), digits++, c = fgetc(f);
+  *out = v;
+  return digits > 0 && digits < 10; /* the single white-space byte after the token has been consumed */
+}
+static inline struct gs_image gs_read_pgm(const char *path) {
+  struct gs_image img = {0, 0, NULL};
+  unsigned w = 0, h = 0, maxval = 0;
+  FILE *f = (path[0] == '-' && !path[1]) ? stdin : fopen(path, "rb");
+  if (!f) return img;
+  if (fgetc(f) == 'P' && fgetc(f) == '5' && gs__pgm_token(f, &w) && gs__pgm_token(f, &h) &&
+      gs__pgm_token(f, &maxval) && maxval == 255) {
+    img = gs_alloc(w, h);
+    if (img.data && fread(img.data, 1, (size_t)w * h, f) != (size_t)w * h) {
+      gs_free(img);
+      img.w = img.h = 0, img.data = NULL;
+    }
+  }
+  if (f != stdin) fclose(f);
+  return img;
+}
+static inline int gs_write_pgm(struct gs_image img, const char *path) {
+  FILE *f;
+  size_t n;
+  if (!gs_valid(img)) return -1;
+  f = (path[0] == '-' && !path[1]) ? stdout : fopen(path, "wb");
+  if (!f) return -1;
+  fprintf(f, "P5\n%u %u\n255\n", img.w, img.h);
+  n = fwrite(img.data, 1, (size_t)img.w * img.h, f);
+  if (f != stdout) fclose(f);
+  else fflush(f);
+  return n == (size_t)img.w * img.h ? 0 : -1;
+}
 #endif
 
 #define gs_for(img, x, y)                \

@@ -328,6 +328,49 @@ def test_reference_unit_tests_run_on_cuda_path():
     assert r.returncode == 0, (r.returncode, r.stdout[-400:], r.stderr[-400:])
 
 
+def test_cli_batch_pipeline(G, O, tmp_path):
+    """gsb_magick: PGM batch in, device-resident pipeline, PGM batch out -- against the oracle chain
+    (the reference Makefile's lena chain plus sobel / filter / resize stages)"""
+    import subprocess
+    from grayskull_b200 import _lib
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "gsb_magick")
+    w, h, n = 320, 200, 3
+    frames = [L.natural_like(w, h, 90 + f) for f in range(n)]
+    paths = []
+    for f, a in enumerate(frames):
+        pth = tmp_path / ("in%d.pgm" % f)
+        pth.write_bytes(b"P5\n%d %d\n255\n" % (w, h) + a.tobytes())
+        paths.append(str(pth))
+
+    def read(pth):
+        b = open(pth, "rb").read()
+        hdr = b.split(b"\n", 3)
+        ww, hh = map(int, hdr[1].split())
+        return np.frombuffer(hdr[3], np.uint8).reshape(hh, ww)
+
+    r = subprocess.run([exe, "blur:2,threshold:otsu,erode:2,dilate:2", str(tmp_path / "a_")] + paths, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for f, a in enumerate(frames):
+        x = o_blur(O, a, 2)
+        t = O.gso_otsu_threshold(L.ptr(x), w, h)
+        x = x.copy(); O.gso_threshold(L.ptr(x), w, h, t)
+        for op in (0, 0, 1, 1):
+            x = o_morph(O, x, op)
+        assert np.array_equal(read(str(tmp_path / ("a_%04d.pgm" % f))), x), f
+    r = subprocess.run([exe, "filter:gaussian,sobel,threshold:otsu+10,downsample,resize:100:37,keypoints:50:20", str(tmp_path / "b_")] + paths,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.count("keypoints") == n
+    for f, a in enumerate(frames):
+        k, norm = L.filter_kernel("gaussian")
+        x = np.zeros_like(a); O.gso_filter(L.ptr(x), L.ptr(a), w, h, L.ptr(k), 3, 3, norm)
+        x = o_sobel(O, x, 0)
+        t = (O.gso_otsu_threshold(L.ptr(x), w, h) + 10) & 255
+        x = x.copy(); O.gso_threshold(L.ptr(x), w, h, t)
+        x = o_resize(O, o_down(O, x), 100, 37)
+        assert np.array_equal(read(str(tmp_path / ("b_%04d.pgm" % f))), x), f
+
+
 def _o_hist(O, a):
     h = np.zeros(256, np.uint32); O.gso_histogram(L.ptr(a), a.shape[1], a.shape[0], L.ptr(h)); return h
 

@@ -99,6 +99,44 @@ def test_standalone_header_compiles_as_c99(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_standalone_header_pgm_io(tmp_path):
+    """P5 reader / writer of the stand-alone header (reference grayskull.h:111-136 semantics): round trip, header
+    with comments and mixed white space, wrong maxval / truncated data rejected"""
+    src = tmp_path / "pgm.c"
+    src.write_text('#include <string.h>\n#include "grayskull.h"\n'
+                   "int main(int argc, char **argv) {\n"
+                   "  struct gs_image a = gs_alloc(5, 3); unsigned i; (void)argc;\n"
+                   "  for (i = 0; i < 15; i++) a.data[i] = (uint8_t)(i * 17 + 10);\n"
+                   "  if (gs_write_pgm(a, argv[1]) != 0) return 2;\n"
+                   "  { struct gs_image b = gs_read_pgm(argv[1]);\n"
+                   "    if (!gs_valid(b) || b.w != 5 || b.h != 3 || memcmp(a.data, b.data, 15)) return 3;\n    gs_free(b); }\n"
+                   "  { struct gs_image c = gs_read_pgm(argv[2]);\n"
+                   "    if (!gs_valid(c) || c.w != 2 || c.h != 2 || c.data[0] != 10 || c.data[3] != 'A') return 4;\n    gs_free(c); }\n"
+                   "  if (gs_valid(gs_read_pgm(argv[3])) || gs_valid(gs_read_pgm(argv[4])) || gs_valid(gs_read_pgm(argv[5]))) return 5;\n"
+                   "  gs_free(a); return 0; }\n")
+    exe = str(tmp_path / "pgm")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                        "-o", exe, str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    (tmp_path / "c.pgm").write_bytes(b"P5\n# made by hand\n2\t2\n# another\n255\n" + bytes([10, 0, 1, 65]))
+    (tmp_path / "bad16.pgm").write_bytes(b"P5\n2 2\n65535\n" + bytes(8))
+    (tmp_path / "short.pgm").write_bytes(b"P5\n4 4\n255\n" + bytes(7))
+    r = subprocess.run([exe, str(tmp_path / "rt.pgm"), str(tmp_path / "c.pgm"), str(tmp_path / "bad16.pgm"),
+                        str(tmp_path / "short.pgm"), str(tmp_path / "missing.pgm")])
+    assert r.returncode == 0
+    assert (tmp_path / "rt.pgm").read_bytes()[:11] == b"P5\n5 3\n255\n"
+
+
+def test_cli_is_built_and_has_no_cpu_path(tmp_path):
+    """gsb_magick (grayskull_b200/cli) builds with the library and refuses to do anything without inputs / a GPU"""
+    from grayskull_b200 import _lib
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "gsb_magick")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe, "blur:2", str(tmp_path / "o"), str(tmp_path / "missing.pgm")], capture_output=True, text=True)
+    assert r.returncode == 1 and "gsb_magick:" in r.stderr
+    assert subprocess.run([exe], capture_output=True).returncode == 1
+
+
 def test_box_division_constants_are_exact():
     """box.cu: fma_rd(2^23 + S, m*2^-24, 2^23 - m/2) == 2^23 + floor(S*m / 2^24), and
     floor(S*m/2^24) == S // count for every count <= 225 and every S <= 255*count."""
