@@ -317,10 +317,10 @@ static int launch_box_r(const CUtensorMap &tmap, uint8_t *dst, unsigned w, unsig
   // tile t covers output columns [240 t - 8, 240 t + 232)
   const unsigned tiles_x = (w + 8 + BX_STRIDE - 1) / BX_STRIDE, tiles_y = (h + BX_TH - 1) / BX_TH;
   GSB_ASSERT(tiles_y <= 65535u && n <= 65535u);   // grid y / z limits (launch_box checks n)
-  static bool configured = false;                 // per instantiation; one device per process
-  if (!configured) {
+  static DeviceOnce once;                         // per instantiation
+  if (once.needed()) {
     GSB_CHECK(cudaFuncSetAttribute(k_box_tma<R, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
-    configured = true;
+    once.done();
   }
   k_box_tma<R, ADAPTIVE><<<dim3(tiles_x, tiles_y, n), BX_THREADS, BX_SMEM, s>>>(tmap, dst, w, h, cparam);
   GSB_LAUNCHED(1);

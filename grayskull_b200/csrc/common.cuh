@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "../../include/grayskull_b200.h"
 
 namespace gsb {
@@ -40,6 +42,20 @@ bool force_generic();  // GS_B200_FORCE_GENERIC=1: never take the TMA-tiled kern
 // Grow-only device scratch, one arena per (device, stream, slot).  Not freed until process
 // exit: the hot path must not cudaMalloc per call.  Returns nullptr on allocation failure.
 void *workspace(cudaStream_t s, int slot, size_t bytes);
+
+// Per-device one-time setup at a call site (function attributes such as the dynamic shared-memory opt-in are
+// per device):   static DeviceOnce once;  if (once.needed()) { ...setup...; once.done(); }
+// Two threads racing on the same device may both run the setup, which is harmless; none skips it.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static unsigned long long bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool needed() const { return !(mask.load(std::memory_order_acquire) & bit()); }
+  void done() { mask.fetch_or(bit(), std::memory_order_release); }
+};
 enum { WS_INTEGRAL = 0, WS_FAST_A, WS_FAST_B, WS_ORB_A, WS_ORB_B, WS_LBP_A, WS_LBP_B, WS_LBP_C,
        WS_STAGE_A, WS_STAGE_B, WS_STAGE_C, WS_STAGE_D, WS_HIST, WS_SLOTS };
 

@@ -205,11 +205,11 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
     GSB_CHECK(cudaMemsetAsync(ctrl, 0, ctrl_bytes, st));
     const unsigned threads = ((w / 8 + 31) / 32) * 32;
     const size_t smem = sizeof(uint32_t) * gsb::IB_BH * threads;   // <= 64 KB
-    static bool configured = false;
-    if (!configured) {
+    static gsb::DeviceOnce once;
+    if (once.needed()) {
       GSB_CHECK(cudaFuncSetAttribute(gsb::k_integral_bands<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
       GSB_CHECK(cudaFuncSetAttribute(gsb::k_integral_bands<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-      configured = true;
+      once.done();
     }
     if (threads <= 512) gsb::k_integral_bands<512><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl);
     else gsb::k_integral_bands<1024><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl);

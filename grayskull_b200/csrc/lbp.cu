@@ -532,13 +532,14 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     uint16_t *t = cur;
     cur = nxt, nxt = t;
   }
-  __syncthreads();
+  // the warp's slots were touched by nobody else: store their mask words and leave -- no CTA barrier
+  __syncwarp();
   const int sx_n = twx >> 5;
-  for (int w = tid; w < twy * sx_n; w += LBP3_THREADS) {
-    const int ly = w / sx_n, sx = w % sx_n;
+  for (int slot = (int)warp + (int)lane * NWARPS; slot < nslots; slot += 32 * NWARPS) {
+    const int ly = slot / sx_n, sx = slot % sx_n;
     const unsigned chunk = (unsigned)(wx0 >> 5) + (unsigned)sx;
     if (wy0 + ly < sc.ny && chunk < sc.chunks)
-      masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[w];
+      masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[slot];
   }
 }
 
@@ -876,10 +877,10 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   const bool v3 = !p->tiles.empty() && reinterpret_cast<uintptr_t>(ii) % 16 == 0 && !gsb::force_generic() &&
                   !(tma_env && tma_env[0] == '0') && getenv("GS_B200_LBP_V1") == nullptr;
   if (v3) {
-    static bool configured3 = false;
-    if (!configured3) {
+    static gsb::DeviceOnce once3;
+    if (once3.needed()) {
       GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      configured3 = true;
+      once3.done();
     }
     GSB_CHECK(cudaMemsetAsync(masks, 0, 4 * (size_t)dc.total_slots * n, st));   // padding slots between scales
     int flat_n = GSB_LBP3_FLAT;
@@ -917,10 +918,10 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   const bool v2 = dc.safe_geometry && smem2 <= 160 * 1024 && (unsigned long long)iw * ih < 0x7FFFFFFFull &&
                   getenv("GS_B200_LBP_V1") == nullptr;
   if (v2) {
-    static size_t configured = 0;
-    if (smem2 > configured) {
-      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      configured = smem2;
+    static gsb::DeviceOnce once2;
+    if (once2.needed()) {                         // the v2 condition above caps smem2 at 160 KB
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      once2.done();
     }
     dim3 grid2((unsigned)(dc.total_slots / gsb::LBP_SLOTS_PER_CTA), n);
     gsb::k_lbp_scan2<<<grid2, gsb::LBP_THREADS, smem2, st>>>(ii, iw, ih, dc, masks);
