@@ -47,6 +47,8 @@ def build(force=False, verbose=False, defines=(), out=None):
     os.makedirs(obj_dir, exist_ok=True)
     newest = _deps_mtime()
     if not force and os.path.exists(lib_out) and os.path.getmtime(lib_out) >= newest:
+        if not out and not os.path.exists(os.path.join(HERE, "gsb_magick")):
+            build_cli()
         return lib_out
     cc = nvcc()
     dflags = ["-D" + d for d in defines]

@@ -252,3 +252,27 @@ FILTER_KERNELS = {   # (weights as int8 rows, norm): the reference's presets (gr
 def filter_kernel(name):
     rows, norm = FILTER_KERNELS[name]
     return np.ascontiguousarray(np.array(rows, np.int8).view(np.uint8)), norm
+
+
+def check_next_golden(impl):
+    """tests/golden/next_golden.npz (made by the REAL reference, tools/make_golden.py) against `impl`, an object
+    with gs_histogram(a), gs_otsu_threshold(a), gs_threshold(a, t), gs_filter(dst, src, kernel_u8, norm),
+    gs_match_template(img, tmpl), gs_find_best_match(res) -> (x, y), gs_orb(a, nkps, t), gs_match_orb(k1, k2, mm, md).
+    Shared by the oracle test (CPU) and the CUDA test (GPU) so the checking logic itself is exercised on both."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "next_golden.npz"))
+    for tag in [str(t) for t in z["tags"]]:
+        a = np.ascontiguousarray(z[tag + "img"])
+        assert np.array_equal(impl.gs_histogram(a), z[tag + "hist"]), tag
+        t = int(z[tag + "otsu"])
+        assert impl.gs_otsu_threshold(a) == t, tag
+        assert np.array_equal(impl.gs_threshold(a.copy(), t), z[tag + "threshold_otsu"]), tag
+        for name in ("sharpen", "emboss", "box", "gaussian", "emboss_norm3", "k5", "k2x4"):
+            k, norm = filter_kernel(name)
+            assert np.array_equal(impl.gs_filter(np.zeros_like(a), a, k, norm), z[tag + "filter_" + name]), (tag, name)
+        res = impl.gs_match_template(a, np.ascontiguousarray(z[tag + "tmpl"]))
+        assert np.array_equal(res, z[tag + "tmatch"]), tag
+        assert tuple(impl.gs_find_best_match(res)) == tuple(int(v) for v in z[tag + "tmatch_best"]), tag
+        ka, kb = impl.gs_orb(a, 300, 20), impl.gs_orb(np.ascontiguousarray(z[tag + "shifted"]), 300, 20)
+        assert ka.tobytes() == z[tag + "kps_a"].tobytes() and kb.tobytes() == z[tag + "kps_b"].tobytes(), tag
+        m = impl.gs_match_orb(ka, kb, 300, 60.0)
+        assert m.tobytes() == z[tag + "matches"].tobytes() and len(m) > 20, tag

@@ -328,6 +328,24 @@ def test_reference_unit_tests_run_on_cuda_path():
     assert r.returncode == 0, (r.returncode, r.stdout[-400:], r.stderr[-400:])
 
 
+def test_golden_next_rows(G):
+    """the 8(f) rows against the reference-generated fixture (tests/golden/next_golden.npz), single-image API"""
+    class Impl:
+        gs_histogram = staticmethod(G.gs_histogram)
+        gs_otsu_threshold = staticmethod(G.gs_otsu_threshold)
+        gs_threshold = staticmethod(G.gs_threshold)
+        gs_filter = staticmethod(G.gs_filter)
+        gs_match_template = staticmethod(G.gs_match_template)
+        gs_find_best_match = staticmethod(G.gs_find_best_match)
+        gs_match_orb = staticmethod(G.gs_match_orb)
+
+        @staticmethod
+        def gs_orb(a, nkps, t):
+            return G.gs_orb_extract(a, nkps, t, np.zeros_like(a))
+
+    L.check_next_golden(Impl)
+
+
 def test_cli_batch_pipeline(G, O, tmp_path):
     """gsb_magick: PGM batch in, device-resident pipeline, PGM batch out -- against the oracle chain
     (the reference Makefile's lena chain plus sobel / filter / resize stages)"""

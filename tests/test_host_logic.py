@@ -129,7 +129,8 @@ def test_standalone_header_pgm_io(tmp_path):
 
 def test_cli_is_built_and_has_no_cpu_path(tmp_path):
     """gsb_magick (grayskull_b200/cli) builds with the library and refuses to do anything without inputs / a GPU"""
-    from grayskull_b200 import _lib
+    from grayskull_b200 import build, _lib
+    build.build()
     exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "gsb_magick")
     assert os.path.exists(exe)
     r = subprocess.run([exe, "blur:2", str(tmp_path / "o"), str(tmp_path / "missing.pgm")], capture_output=True, text=True)

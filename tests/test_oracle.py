@@ -332,6 +332,51 @@ def _read_pgm(path):
         return np.frombuffer(f.read(w * h), np.uint8).reshape(h, w).copy()
 
 
+class _OracleImpl:
+    """the oracle behind the interface _libs.check_next_golden expects"""
+
+    @staticmethod
+    def gs_histogram(a):
+        h = np.zeros(256, np.uint32); O.gso_histogram(L.ptr(a), a.shape[1], a.shape[0], L.ptr(h)); return h
+
+    @staticmethod
+    def gs_otsu_threshold(a):
+        return O.gso_otsu_threshold(L.ptr(a), a.shape[1], a.shape[0])
+
+    @staticmethod
+    def gs_threshold(a, t):
+        O.gso_threshold(L.ptr(a), a.shape[1], a.shape[0], t); return a
+
+    @staticmethod
+    def gs_filter(dst, src, k, norm):
+        O.gso_filter(L.ptr(dst), L.ptr(src), src.shape[1], src.shape[0], L.ptr(k), k.shape[1], k.shape[0], norm); return dst
+
+    @staticmethod
+    def gs_match_template(img, tmpl):
+        res = np.zeros((img.shape[0] - tmpl.shape[0] + 1, img.shape[1] - tmpl.shape[1] + 1), np.uint8)
+        O.gso_match_template(L.ptr(img), img.shape[1], img.shape[0], L.ptr(tmpl), tmpl.shape[1], tmpl.shape[0], L.ptr(res))
+        return res
+
+    @staticmethod
+    def gs_find_best_match(res):
+        b = O.gso_find_best_match(L.ptr(res), res.shape[1], res.shape[0]); return (b % res.shape[1], b // res.shape[1])
+
+    @staticmethod
+    def gs_orb(a, nkps, t):
+        return o_orb(a, np.zeros_like(a), nkps, t)
+
+    @staticmethod
+    def gs_match_orb(k1, k2, mm, md):
+        m = np.zeros(max(mm, 1), L.MATCH_DTYPE)
+        n = O.gso_match_orb(L.ptr(k1), len(k1), L.ptr(k2 if len(k2) else np.zeros(1, L.KP_DTYPE)), len(k2), L.ptr(m), mm, md)
+        return m[:n]
+
+
+def test_golden_next_rows():
+    """tests/golden/next_golden.npz: the 8(f) rows as computed by the real reference on lena and two synthetic images"""
+    L.check_next_golden(_OracleImpl)
+
+
 def test_golden_lena():
     """tests/golden/lena_golden.npz was produced by the real reference (tools/make_golden.py)"""
     z = np.load(os.path.join(GOLD, "lena_golden.npz"))

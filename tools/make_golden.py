@@ -5,6 +5,8 @@ The GPU box has no /root/reference, so these small fixtures are committed.
 
   lena_golden.npz     every hot-path op on testdata/lena.pgm (128x128; BASELINE config C1)
   random_golden.npz   a handful of odd-sized random images (ragged widths, tiny sizes)
+  next_golden.npz     the SURVEY.md 8(f) rows (gs_match_orb, histogram / Otsu / threshold, gs_filter,
+                      gs_match_template / gs_find_best_match) on lena and two synthetic images
 """
 import hashlib
 import os
@@ -50,6 +52,37 @@ def run_all(R, a, cas_ptr, tag, out, orb_nkps=500, lbp=True):
         out[tag + "lbp_rects"] = r[:n].copy()
 
 
+def run_next(R, a, tag, out, rng):
+    """reference outputs for the 8(f) rows; inputs that are not derivable from `a` are stored too"""
+    h, w = a.shape
+    hist = np.zeros(256, np.uint32); R.gs_histogram(L.img(a), L.ptr(hist)); out[tag + "hist"] = hist
+    t = int(R.gs_otsu_threshold(L.img(a))); out[tag + "otsu"] = np.array(t)
+    d = a.copy(); R.gs_threshold(L.img(d), t); out[tag + "threshold_otsu"] = d
+    for name in ("sharpen", "emboss", "box", "gaussian", "emboss_norm3", "k5", "k2x4"):
+        k, norm = L.filter_kernel(name)
+        d = np.zeros_like(a); R.gs_filter(L.img(d), L.img(a), L.img(k), norm); out[tag + "filter_" + name] = d
+    th, tw = min(h, 21), min(w, 30)
+    y0, x0 = (h - th) // 3, (w - tw) // 2
+    tmpl = np.clip(a[y0:y0 + th, x0:x0 + tw].astype(np.int16) + rng.integers(-2, 3, (th, tw)), 0, 255).astype(np.uint8)
+    out[tag + "tmpl"] = tmpl
+    res = np.zeros((h - th + 1, w - tw + 1), np.uint8)
+    R.gs_match_template(L.img(a), L.img(tmpl), L.img(res)); out[tag + "tmatch"] = res
+    p = R.gs_find_best_match(L.img(res)); out[tag + "tmatch_best"] = np.array([p.x, p.y])
+    # ORB keypoints of the image and of a shifted, slightly noisy copy, matched with the 0.8 ratio test
+    b = np.roll(a, (2, 3), axis=(0, 1))
+    b = np.clip(b.astype(np.int16) + rng.integers(-2, 3, b.shape), 0, 255).astype(np.uint8)
+    out[tag + "shifted"] = b
+    ks = []
+    for im in (a, b):
+        sm = np.zeros_like(im); k = np.zeros(300, L.KP_DTYPE)
+        n = R.gs_orb_extract(L.img(im), L.ptr(k), 300, 20, L.ptr(sm)); ks.append(k[:n].copy())
+    out[tag + "kps_a"], out[tag + "kps_b"] = ks
+    m = np.zeros(300, L.MATCH_DTYPE)
+    n = R.gs_match_orb(L.ptr(ks[0]), len(ks[0]), L.ptr(ks[1] if len(ks[1]) else np.zeros(1, L.KP_DTYPE)), len(ks[1]), L.ptr(m), 300, 60.0)
+    out[tag + "matches"] = m[:n].copy()
+    return n
+
+
 def main():
     R = L.ref()
     cas = R.ref_frontalface()
@@ -71,6 +104,15 @@ def main():
         out["img%d" % i] = a
         run_all(R, a, cas, "i%d_" % i, out, orb_nkps=200, lbp=(w >= 24 and h >= 24))
     np.savez_compressed(os.path.join(gold, "random_golden.npz"), **out)
+
+    rng = np.random.default_rng(2027)
+    out = {"tags": np.array(["lena_", "nat_", "rnd_"])}
+    imgs = {"lena_": lena, "nat_": L.natural_like(200, 120, 7), "rnd_": rng.integers(0, 256, (50, 77)).astype(np.uint8)}
+    for tag, a in imgs.items():
+        out[tag + "img"] = a
+        n = run_next(R, a, tag, out, rng)
+        print("%s %d matches, otsu %d, best %s" % (tag, n, int(out[tag + "otsu"]), out[tag + "tmatch_best"]))
+    np.savez_compressed(os.path.join(gold, "next_golden.npz"), **out)
     print("wrote", gold)
 
 
