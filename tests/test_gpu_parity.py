@@ -389,6 +389,61 @@ def test_cli_batch_pipeline(G, O, tmp_path):
         assert np.array_equal(read(str(tmp_path / ("b_%04d.pgm" % f))), x), f
 
 
+def test_reference_cli_overlay_vs_cpu(tmp_path):
+    """The reference's own CLI (examples/nanomagick/nanomagick.c, unmodified) built twice by oracle/Makefile: as
+    upstream builds it, and in overlay mode against libgrayskull_b200.so.  The command lines of the reference
+    Makefile's `testdata` target (on lena from the fixture and synthetic stand-ins for its other images) must
+    give the same exit codes, the same stdout and byte-identical PGMs from both."""
+    import subprocess
+    ref_dir = os.path.join(L.ORACLE_DIR, "_ref")
+    exes = {k: os.path.join(ref_dir, "nanomagick_" + k) for k in ("cpu", "overlay")}
+    if not all(os.path.exists(e) for e in exes.values()):
+        pytest.skip("nanomagick builds not present (need the reference tree at build time)")
+
+    def pgm(path, a):
+        path.write_bytes(b"P5\n%d %d\n255\n" % (a.shape[1], a.shape[0]) + a.tobytes())
+
+    lena = np.load(os.path.join(GOLD, "lena_golden.npz"))["lena"]
+    pgm(tmp_path / "lena.pgm", lena)
+    pgm(tmp_path / "nat.pgm", L.natural_like(320, 240, 11))
+    rng = np.random.default_rng(5)
+    doc = np.full((300, 400), 40, np.int16) + rng.integers(-8, 9, (300, 400))
+    yy, xx = np.mgrid[0:300, 0:400]
+    inside = (yy > 40 + xx * 0.05) & (yy < 250 - xx * 0.04) & (xx > 60 + yy * 0.08) & (xx < 340 - yy * 0.03)
+    doc[inside] = 210 + rng.integers(-10, 11, int(inside.sum()))
+    doc[inside & (yy % 12 < 3) & (xx % 9 < 6)] = 60                     # "text"
+    pgm(tmp_path / "doc.pgm", np.clip(doc, 0, 255).astype(np.uint8))
+    marks = np.full((240, 320), 200, np.uint8)
+    for (y, x) in ((30, 40), (30, 200), (150, 60), (140, 220)):
+        marks[y:y + 50, x:x + 50] = 20; marks[y + 10:y + 40, x + 10:x + 40] = 230
+    pgm(tmp_path / "marks.pgm", np.clip(marks.astype(np.int16) + rng.integers(-6, 7, marks.shape), 0, 255).astype(np.uint8))
+
+    cmds = [("identify", "{i}lena.pgm"), ("resize 128 64", "{i}lena.pgm {o}r.pgm"), ("crop 32 32 64 64", "{i}lena.pgm {o}c.pgm"),
+            ("blur 1", "{i}lena.pgm {o}b1.pgm"), ("blur 9", "{i}lena.pgm {o}b9.pgm"), ("threshold 128", "{o}b1.pgm {o}t128.pgm"),
+            ("threshold otsu", "{o}b1.pgm {o}otsu.pgm"), ("adaptive 15 5", "{i}lena.pgm {o}ad.pgm"),
+            ("morph erode 2", "{o}otsu.pgm {o}er.pgm"), ("morph dilate 2", "{o}er.pgm {o}di.pgm"), ("sobel", "{i}lena.pgm {o}so.pgm"),
+            ("blur 3", "{i}marks.pgm {o}m1.pgm"), ("sobel", "{o}m1.pgm {o}m2.pgm"), ("threshold otsu", "{o}m2.pgm {o}m3.pgm"),
+            ("morph dilate 9", "{o}m3.pgm {o}m4.pgm"), ("morph erode 10", "{o}m4.pgm {o}m5.pgm"), ("blobs 150", "{o}m5.pgm {o}m6.pgm"),
+            ("scan", "{i}doc.pgm {o}scan.pgm"), ("keypoints 100 20", "{i}nat.pgm {o}kp.pgm"),
+            ("orb {o}c.pgm", "{i}lena.pgm {o}orb.pgm"), ("faces 1", "{i}lena.pgm {o}f1.pgm"), ("faces 2", "{i}lena.pgm {o}f2.pgm")]
+    outs = {}
+    for kind, exe in exes.items():
+        od = tmp_path / kind
+        od.mkdir()
+        log = []
+        for verb, files in cmds:
+            line = (verb + " " + files).format(i=str(tmp_path) + "/", o=str(od) + "/")
+            r = subprocess.run([exe] + line.split(), capture_output=True, timeout=300)
+            log.append((verb, r.returncode, r.stdout.replace(str(od).encode(), b"<out>")))
+        outs[kind] = (log, {p.name: p.read_bytes() for p in sorted(od.iterdir())})
+    (log_c, files_c), (log_o, files_o) = outs["cpu"], outs["overlay"]
+    assert log_c == log_o
+    assert all(rc == 0 for _, rc, _ in log_c), [(v, rc) for v, rc, _ in log_c if rc]
+    assert sorted(files_c) == sorted(files_o) and len(files_c) >= 20
+    for name in files_c:
+        assert files_c[name] == files_o[name], name
+
+
 def _o_hist(O, a):
     h = np.zeros(256, np.uint32); O.gso_histogram(L.ptr(a), a.shape[1], a.shape[0], L.ptr(h)); return h
 
