@@ -377,6 +377,50 @@ def test_golden_next_rows():
     L.check_next_golden(_OracleImpl)
 
 
+def test_survey_appendix_b_values(tmp_path):
+    """values the reference produced on testdata/lena.pgm when the survey was written, checked
+    against the committed fixture (which the GPU golden tests compare the CUDA path with) and against the oracle"""
+    z = np.load(os.path.join(GOLD, "lena_golden.npz"))
+    a = z["lena"]
+
+    def pgm_md5(img):
+        return hashlib.md5(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]) + img.tobytes()).hexdigest()
+
+    assert pgm_md5(a) == "66bd37186e4510052eefa3a52eef8188"
+    assert pgm_md5(z["sobel"]) == "27cd5834468e2c0351475aacb7b5fc29" == pgm_md5(o_sobel(a))
+    assert pgm_md5(z["blur1"]) == "53bfdf15397839728afd776749848584" == pgm_md5(o_blur(a, 1))
+    assert pgm_md5(o_blur(a, 5)) == "24dd5d5b6898d8e6328410fa28c5e1f6" == pgm_md5(z["blur5"])
+    assert pgm_md5(z["blur9"]) == "8c9c1e0db5ee451f7044b9bb96dcdb35"
+    assert pgm_md5(z["adaptive_15_5"]) == "b4de7a7037676f5808c892b353362d4d" == pgm_md5(o_adaptive(a, 15, 5))
+    assert pgm_md5(z["resize_128x64"]) == "96b030c4a2a50011a27efdfd5212a790" == pgm_md5(o_resize(a, 128, 64))
+    k = z["fast_kps"]
+    assert len(k) == 325 and (k[0]["x"], k[0]["y"], k[0]["response"]) == (56, 11, 2)
+    assert (k[-1]["x"], k[-1]["y"], k[-1]["response"]) == (24, 124, 14)
+    k = o_orb(a, np.zeros_like(a), 500, 20)
+    assert k.tobytes() == z["orb_kps"].tobytes() and len(k) == 280
+    assert (k[0]["x"], k[0]["y"], k[0]["response"]) == (49, 65, 63) and k[0]["descriptor"][0] == 0x6ebed143
+    assert abs(float(k[0]["angle"]) - 0.3026622) < 1e-6
+    r = z["lbp_rects"]
+    assert len(r) == 10 and [tuple(int(v) for v in r[i]) for i in range(5)] == [
+        (54, 52, 46, 46), (52, 46, 51, 51), (48, 48, 51, 51), (54, 48, 51, 51), (52, 50, 51, 51)]
+    ii = o_integral(a)
+    assert len(o_detect(L.HostCascade(), ii, 1000, 1.2, 1.0, 4.0, 1)) == 20
+    # the reference CLI built as upstream builds it (oracle/_ref/nanomagick_cpu); the GPU suite checks that the
+    # overlay build reproduces this binary's outputs byte for byte
+    exe = os.path.join(L.ORACLE_DIR, "_ref", "nanomagick_cpu")
+    if os.path.exists(exe):
+        import subprocess
+        src = tmp_path / "lena.pgm"
+        src.write_bytes(b"P5\n128 128\n255\n" + a.tobytes())
+        for args, md5 in ((["keypoints", "100", "20"], "c3745a335c3f6d53da8fe13cadf3c9a9"), (["faces", "2"], "0fdde3c4c3121ebe696b2e9100615e6e"),
+                          (["sobel"], "27cd5834468e2c0351475aacb7b5fc29")):
+            out = tmp_path / "o.pgm"
+            assert subprocess.run([exe] + args + [str(src), str(out)], capture_output=True).returncode == 0
+            assert hashlib.md5(out.read_bytes()).hexdigest() == md5, args
+        r = subprocess.run([exe, "orb", str(src), str(src), str(tmp_path / "orb.pgm")], capture_output=True, text=True)
+        assert "Template: 340 keypoints, Scene: 340 keypoints, Matches: 300" in r.stdout
+
+
 def test_golden_lena():
     """tests/golden/lena_golden.npz was produced by the real reference (tools/make_golden.py)"""
     z = np.load(os.path.join(GOLD, "lena_golden.npz"))
