@@ -138,6 +138,30 @@ def test_cli_is_built_and_has_no_cpu_path(tmp_path):
     assert subprocess.run([exe], capture_output=True).returncode == 1
 
 
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: one JSON line with the contract's keys, timed on the host cores; under torchrun
+    only rank 0 works and prints"""
+    import json
+    import sys
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Mpixels/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env.update(RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
 def test_box_division_constants_are_exact():
     """box.cu: fma_rd(2^23 + S, m*2^-24, 2^23 - m/2) == 2^23 + floor(S*m / 2^24), and
     floor(S*m/2^24) == S // count for every count <= 225 and every S <= 255*count."""
