@@ -77,6 +77,9 @@ def build(force=False, verbose=False, defines=(), out=None):
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     if not out:
         build_cli()
+    if out:   # experiment variants: their object files are not worth keeping (or shipping with gpurun)
+        import shutil
+        shutil.rmtree(obj_dir, ignore_errors=True)
     return lib_out
 
 
