@@ -527,6 +527,38 @@ GSO_API unsigned gso_lbp_window(const struct gs_lbp_cascade *c, const uint32_t *
   return 1;
 }
 
+/* Analysis helper (not part of the reference API): for every window position of ONE scale, the number of
+ * cascade stages the window passes (nstages = a detection).  Same walk as gso_lbp_window; feeds the
+ * divergence / load-balance model in tools/lbp_model.py.  out: ny x nx bytes, ny = (ih - win_h) / step + 1. */
+GSO_API void gso_lbp_depth_map(const struct gs_lbp_cascade *c, const uint32_t *ii, unsigned iw, unsigned ih,
+                               float scale, int step, uint8_t *out) {
+  int win_w = (int)((float)c->window_w * scale), win_h = (int)((float)c->window_h * scale);
+  if (win_w > (int)iw || win_h > (int)ih) return;
+  size_t k = 0;
+  for (int y = 0; y + win_h <= (int)ih; y += step)
+    for (int x = 0; x + win_w <= (int)iw; x += step) {
+      int si = 0;
+      for (; si < c->nstages; si++) {
+        int start = c->stage_weak_start[si], n = c->stage_nweaks[si];
+        float sum = 0.0f;
+        for (int i = 0; i < n; i++) {
+          int wi = start + i, fi = c->weak_feature_idx[wi];
+          int fx = (int)((float)c->features[fi * 4 + 0] * scale), fy = (int)((float)c->features[fi * 4 + 1] * scale);
+          int fw = (int)((float)c->features[fi * 4 + 2] * scale), fh = (int)((float)c->features[fi * 4 + 3] * scale);
+          if (fw < 1) fw = 1;
+          if (fh < 1) fh = 1;
+          int code = lbp_code(ii, iw, x + fx, y + fy, fw, fh);
+          int idx = code >> 5, bit = code & 31;
+          int match = idx < (int)c->weak_num_subsets[wi] &&
+                      ((uint32_t)c->subsets[c->weak_subset_offset[wi] + idx] >> bit & 1u);
+          sum += match ? c->weak_left_val[wi] : c->weak_right_val[wi];
+        }
+        if (sum < c->stage_threshold[si]) break;
+      }
+      out[k++] = (uint8_t)si;
+    }
+}
+
 /* gs_lbp_detect, grayskull.h:815-835: scales by repeated fp32 multiply, (scale, y, x) order,
  * hard stop at max_rects */
 GSO_API unsigned gso_lbp_detect(const struct gs_lbp_cascade *c, const uint32_t *ii, unsigned iw,

@@ -81,6 +81,8 @@ def oracle():
         lib.gso_atan2f.restype = C.c_float
         lib.gso_atan2f.argtypes = [C.c_float, C.c_float]
         lib.gso_match_orb.restype = C.c_uint
+        lib.gso_lbp_depth_map.restype = None
+        lib.gso_lbp_depth_map.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_int, C.c_void_p]
         lib.gso_filter.restype = None
         lib.gso_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
         lib.gso_match_template.restype = None
