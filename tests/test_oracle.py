@@ -212,6 +212,23 @@ def test_diff_lbp():
             assert R.gs_lbp_window(ref_c, L.ptr(ii), w, h, x, y, s) == O.gso_lbp_window(cas.ptr, L.ptr(ii), w, h, x, y, s)
 
 
+def test_lbp_depth_map_agrees_with_window():
+    """gso_lbp_depth_map (analysis helper for tools/lbp_model.py): depth == nstages exactly where the window fires"""
+    cas = L.HostCascade()
+    nst = len(cas.arrays["stage_threshold"])
+    a = L.natural_like(160, 120, 21)
+    ii = o_integral(a)
+    for s in (1.0, 1.5):
+        s = float(np.float32(s)); win = int(np.float32(24) * np.float32(s))
+        nx, ny = (160 - win) // 2 + 1, (120 - win) // 2 + 1
+        depth = np.zeros((ny, nx), np.uint8)
+        O.gso_lbp_depth_map(cas.ptr, L.ptr(ii), 160, 120, s, 2, L.ptr(depth))
+        assert depth.max() <= nst and (depth == 0).any()
+        for yi in range(0, ny, 3):
+            for xi in range(0, nx, 3):
+                assert (depth[yi, xi] == nst) == bool(O.gso_lbp_window(cas.ptr, L.ptr(ii), 160, 120, 2 * xi, 2 * yi, s))
+
+
 @needs_ref
 def test_diff_match_orb():
     R = L.ref(); rng = np.random.default_rng(6)
