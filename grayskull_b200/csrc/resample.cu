@@ -63,6 +63,9 @@ constexpr int RS_ROWS = 8;
 #ifndef GSB_RS_PAIRS
 #define GSB_RS_PAIRS 1
 #endif
+#ifndef GSB_RS_PIPE
+#define GSB_RS_PIPE 0
+#endif
 
 __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c11, float omx, float dx, float omy,
                                         float dy) {
@@ -94,6 +97,35 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
   for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
     const uint8_t *s = src + (size_t)f * sw * sh;
     uint8_t *d = dst + (size_t)f * dw * dh;
+#if GSB_RS_PIPE
+    // EXPERIMENT (not measured yet, off by default): the row loop below computes one row's y coefficients (an
+    // IEEE division), then loads, then interpolates -- a serial latency chain per row.  Here all RS_ROWS rows'
+    // coefficients come first, then all 2 x RS_ROWS 64-bit loads are in flight together, then the arithmetic.
+    if (pairs && yb + RS_ROWS <= dh) {
+      float dyv[RS_ROWS];
+      uint2 av[RS_ROWS], bv[RS_ROWS];
+#pragma unroll
+      for (int r = 0; r < RS_ROWS; r++) {
+        unsigned y0, y1;
+        resize_axis(yb + r, sh, dh, y0, y1, dyv[r]);
+        av[r] = __ldg(reinterpret_cast<const uint2 *>(s + (size_t)y0 * sw + x0[0]));
+        bv[r] = __ldg(reinterpret_cast<const uint2 *>(s + (size_t)y1 * sw + x0[0]));
+      }
+#pragma unroll
+      for (int r = 0; r < RS_ROWS; r++) {
+        const uint2 a = av[r], b = bv[r];
+        const float dy = dyv[r], omy = __fsub_rn(1.0f, dy);
+        const float p0 = bilerp(byte_f(a.x, 0), byte_f(a.x, 1), byte_f(b.x, 0), byte_f(b.x, 1), omx[0], dx[0], omy, dy);
+        const float p1 = bilerp(byte_f(a.x, 2), byte_f(a.x, 3), byte_f(b.x, 2), byte_f(b.x, 3), omx[1], dx[1], omy, dy);
+        const float p2 = bilerp(byte_f(a.y, 0), byte_f(a.y, 1), byte_f(b.y, 0), byte_f(b.y, 1), omx[2], dx[2], omy, dy);
+        const float p3 = bilerp(byte_f(a.y, 2), byte_f(a.y, 3), byte_f(b.y, 2), byte_f(b.y, 3), omx[3], dx[3], omy, dy);
+        *reinterpret_cast<uint32_t *>(d + (size_t)(yb + r) * dw + x) =
+            (__float2uint_rz(p0) & 0xFFu) | ((__float2uint_rz(p1) & 0xFFu) << 8) | ((__float2uint_rz(p2) & 0xFFu) << 16) |
+            ((__float2uint_rz(p3) & 0xFFu) << 24);
+      }
+      continue;
+    }
+#endif
     for (unsigned r = 0; r < (unsigned)RS_ROWS && yb + r < dh; r++) {
       const unsigned y = yb + r;
       unsigned y0, y1;
