@@ -177,6 +177,111 @@ def test_box_division_constants_are_exact():
         assert (S.max() * m) / 2 ** 24 < 2 ** 23
 
 
+def test_filter_magic_division_is_exact():
+    """filter.cu fast path: for norm >= 2, min(255, umulhi((u32)sum, floor(2^32/norm)+1)) equals the reference's
+    `sum = sum / norm` (int converted to unsigned, quotient back to int, clamp 0..255) for every sum the host check
+    admits: pos_max * norm < 2^32 and (2^32 - neg_max) / norm >= 256"""
+    rng = np.random.default_rng(41)
+
+    def ref(sv, norm):
+        q = (sv.astype(np.int64) & 0xFFFFFFFF) // norm            # (unsigned)sum / norm
+        v = np.where(q >= 1 << 31, q - (1 << 32), q)              # back into an int
+        return np.clip(v, 0, 255)
+
+    def fast(sv, norm):
+        m = (1 << 32) // norm + 1
+        hi = ((sv.astype(np.int64) & 0xFFFFFFFF).astype(object) * m) >> 32
+        return np.minimum(np.array(hi, dtype=np.int64), 255)
+
+    cases = [(9, 255 * 9, 0), (16, 255 * 16, 0), (3, 255 * 4, 255 * 4), (7, 255 * 127 * 5, 255 * 128 * 4), (2, 32385 * 9, 32640 * 9),
+             (255, 65025, 3000), (4096, 255 * 127 * 9, 255 * 128 * 9)]
+    for _ in range(40):
+        norm = int(rng.integers(2, 1 << int(rng.integers(2, 24))))
+        pos = int(rng.integers(0, min((1 << 32) // norm, 255 * 127 * 9) + 1))
+        neg = int(rng.integers(0, 255 * 128 * 9 + 1))
+        cases.append((norm, pos, neg))
+    checked = 0
+    for norm, pos, neg in cases:
+        if not (pos * norm < (1 << 32) and ((1 << 32) - neg) // norm >= 256):
+            continue                                               # the host sends these to the generic kernel
+        if pos + neg <= 400000:
+            sv = np.arange(-neg, pos + 1, dtype=np.int64)
+        else:
+            sv = np.unique(np.concatenate([rng.integers(-neg, pos + 1, 200000), np.arange(-min(neg, 2000), min(pos, 2000) + 1),
+                                           np.arange(max(pos - 2000, 0), pos + 1), np.arange(-neg, min(-neg + 2000, 0) + 1),
+                                           (np.arange(0, pos // norm + 1)[:5000] * norm), (np.arange(1, pos // norm + 1)[:5000] * norm - 1)]))
+        assert np.array_equal(fast(sv, norm), ref(sv, norm)), (norm, pos, neg)
+        checked += 1
+    assert checked >= 20
+
+
+def test_otsu_parallel_form_matches_sequential_scan():
+    """histogram.cu k_otsu: serial prefix sums + per-threshold variance + FIRST-maximum reduction over the valid
+    thresholds must pick the same threshold as the reference's sequential loop (checked through the oracle)"""
+    import _libs as L
+    O = L.oracle()
+    rng = np.random.default_rng(42)
+    f32 = np.float32
+    for it in range(300):
+        hist = (rng.integers(0, 1 << int(rng.integers(1, 22)), 256) * (rng.random(256) < rng.random())).astype(np.uint32)
+        if it % 7 == 0:
+            hist[:] = 0; hist[int(rng.integers(0, 256))] = 1000           # one level only
+        if it % 11 == 0:
+            hist[int(rng.integers(0, 128))] = hist[int(rng.integers(128, 256))] = 77777   # exact ties are likely
+        npix = int(hist.sum())
+        if npix == 0:
+            continue
+        total = f32(0)
+        for i in range(256):
+            total = f32(total + f32(f32(i) * f32(hist[i])))
+        wb = np.cumsum(hist.astype(np.int64))
+        sum_b = np.zeros(256, f32); acc = f32(0)
+        for t in range(256):
+            acc = f32(acc + f32(f32(t) * f32(hist[t]))); sum_b[t] = acc
+        wf = npix - wb
+        valid = (wb > 0) & (wf > 0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            m_b = (sum_b / wb.astype(f32)).astype(f32)
+            m_f = ((f32(total) - sum_b).astype(f32) / wf.astype(f32)).astype(f32)
+            diff = (m_b - m_f).astype(f32)
+            var = (((wb.astype(f32) * wf.astype(f32)).astype(f32) * diff).astype(f32) * diff).astype(f32)
+        best = 0
+        if valid.any():
+            v = np.where(valid, var, f32(-1))
+            best = int(np.argmax(v))                                      # first maximum
+        assert best == O.gso_otsu_from_hist(L.ptr(hist), npix), it
+
+
+def test_match_key_trick_matches_sequential_scan():
+    """match.cu: the two smallest (distance << 22 | index) keys with M represented by ceil(M) << 22 reproduce the
+    reference's float scan (best / second / first best index, acceptance test) for any max_distance"""
+    rng = np.random.default_rng(43)
+    f32 = np.float32
+    for it in range(3000):
+        n2 = int(rng.integers(0, 40))
+        d = rng.integers(0, 257, n2) if it % 3 else rng.integers(0, 8, n2)
+        md = f32(rng.choice([0.0, 0.5, 3.0, 7.0, 60.0, 64.5, 255.0, 255.5, 256.0, 300.0, -1.0, -0.5, 0.99, 1e9]))
+        M = f32(md + f32(1))
+        best, second, bidx = M, M, 0
+        for j, dj in enumerate(d):
+            fd = f32(dj)
+            if fd < best:
+                second, best, bidx = best, fd, j
+            elif fd < second:
+                second = fd
+        accept_ref = bool(best <= md and best < f32(f32(0.8) * second))
+        thr = int(min(max(np.ceil(float(M)), 0.0), 257.0))
+        sentinel = thr << 22
+        keys = sorted([sentinel, sentinel] + [(int(dj) << 22) + j for j, dj in enumerate(d)])
+        b, s2 = keys[0], keys[1]
+        fb = M if b >= sentinel else f32(b >> 22)
+        fs = M if s2 >= sentinel else f32(s2 >> 22)
+        accept = bool(fb <= md and fb < f32(f32(0.8) * fs))
+        assert accept == accept_ref and fb == best and fs == second, (it, md, list(d))
+        if accept:
+            assert (b & ((1 << 22) - 1)) == bidx
+
+
 def test_lbp_window_count_matches_enumeration():
     cas = L.HostCascade()
     # (the reference's loops, enumerated in python with fp32 arithmetic)
