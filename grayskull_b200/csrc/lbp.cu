@@ -907,6 +907,7 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
     // frames go through in chunks so that the de-interleaved copy stays small (<= 1 GiB of workspace)
     const size_t frame_bytes = (size_t)iw * ih * 4;
     unsigned chunk = (unsigned)(((size_t)1 << 30) / frame_bytes);
+    if (const char *ce = getenv("GS_B200_LBP_CHUNK_FRAMES")) chunk = (unsigned)atoi(ce);   // test hook
     chunk = chunk < 1 ? 1 : (chunk > n ? n : chunk);
     uint32_t *planes = static_cast<uint32_t *>(gsb::workspace(st, gsb::WS_LBP_C, frame_bytes * chunk));
     if (!planes) return (int)cudaErrorMemoryAllocation;

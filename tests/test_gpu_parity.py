@@ -267,6 +267,25 @@ def test_lbp_vs_oracle(G, O, cas):
                 assert got[i].tobytes() == want.tobytes(), ("lbp", w, h, mr, sf, i, len(got[i]), len(want))
 
 
+def test_lbp_frame_chunks(G, O, cas):
+    """k_lbp_scan3 takes big batches through its parity-plane workspace in chunks of frames (1 GiB worth);
+    GS_B200_LBP_CHUNK_FRAMES forces small chunks so that a 5-frame batch crosses chunk boundaries (2 + 2 + 1)"""
+    w, h, n = 320, 240, 5
+    frames = np.stack([L.natural_like(w, h, 60 + i) for i in range(n)])
+    ii = np.stack([o_integral(O, f) for f in frames])
+    iid = dev(ii.view(np.int32))
+    os.environ["GS_B200_LBP_CHUNK_FRAMES"] = "2"
+    try:
+        rects, counts = G.lbp_detect_batch(cas, iid, 1000, 1.1, 1.0, 4.0, 2)
+        got = G.rects_to_numpy(rects, counts)
+    finally:
+        del os.environ["GS_B200_LBP_CHUNK_FRAMES"]
+    for i in range(n):
+        want = o_detect(O, cas, ii[i], 1000, 1.1, 1.0, 4.0, 2)
+        assert got[i].tobytes() == want.tobytes(), (i, len(got[i]), len(want))
+    assert sum(len(g) for g in got) > 0
+
+
 # ---- BASELINE.json sizes: crop checks and size-independent properties ------------------------
 def _crop_check(full_out, frame, fn, r, rng, ncrops=6, size=160):
     h, w = frame.shape
