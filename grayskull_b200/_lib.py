@@ -98,6 +98,7 @@ SIGNATURES = {
     "gs_b200_fast_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_orb_extract_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_set_trig_mode": (None, [_i]),
+    "gs_b200_trig_selfcheck": (_i, []),
     "gs_b200_filter_batch": (_i, [_p, _p, _u, _u, _u, _p, _u, _u, _u, _p]),
     "gs_b200_match_template_batch": (_i, [_p, _p, _u, _u, _u, _p, _u, _u, _p]),
     "gs_b200_find_best_match_batch": (_i, [_p, _p, _u, _u, _u, _p]),

@@ -1,5 +1,9 @@
 // api.cu -- the reference's single-image gs_* entry points (include/grayskull.h) on top of the
-// batched kernels: n == 1, legacy default stream, synchronous.  Device / managed pointers are
+// batched kernels: n == 1, synchronous.  Re-entrant like the reference (SURVEY.md 8b "Threading"): every host
+// thread works on its OWN stream per device -- and, because the library's scratch arenas are keyed by (device,
+// stream, slot), on its own staging arenas -- so concurrent gs_* calls from several threads never share a
+// buffer.  The per-thread streams are ordinary blocking streams: they keep the implicit ordering with work the
+// caller queued on the legacy default stream (e.g. a gs_b200_*_batch call with stream NULL on the same images).  Device / managed pointers are
 // used in place; plain host pointers are staged through the library's device workspace (copied
 // in, processed, copied back), so unmodified callers such as the reference's test.c work.
 // Precondition checks are the reference's gs_assert conditions (cited), CUDA failures abort with
@@ -43,6 +47,29 @@ bool on_device(const void *p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// this thread's stream on the current device (created on first use, destroyed with the thread)
+struct ThreadStreams {
+  cudaStream_t s[64] = {};
+  ~ThreadStreams() {
+    for (int d = 0; d < 64; d++)
+      if (s[d]) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;   // runtime already shut down
+        if (cur != d) cudaSetDevice(d);
+        cudaStreamDestroy(s[d]);
+        if (cur != d) cudaSetDevice(cur);
+      }
+  }
+};
+thread_local ThreadStreams t_streams;
+cudaStream_t S() {
+  int dev = 0;
+  GS_CUDA(cudaGetDevice(&dev));
+  cudaStream_t &st = t_streams.s[dev & 63];
+  if (!st) GS_CUDA(cudaStreamCreate(&st));
+  return st;
+}
+
 inline int gs_ok(struct gs_image img) { return img.data && img.w > 0 && img.h > 0; }
 
 // a buffer that lives on the device for the duration of one call
@@ -59,16 +86,16 @@ Buf in_buf(const void *p, size_t bytes, int slot, bool copy_in = true) {
     b.dev = const_cast<void *>(p);
     return b;
   }
-  b.dev = gsb::workspace(0, slot, bytes);
+  b.dev = gsb::workspace(S(), slot, bytes);
   if (!b.dev) die("device workspace allocation", 1);
   b.host = const_cast<void *>(p);
-  if (copy_in) GS_CUDA(cudaMemcpyAsync(b.dev, p, bytes, cudaMemcpyHostToDevice, 0));
+  if (copy_in) GS_CUDA(cudaMemcpyAsync(b.dev, p, bytes, cudaMemcpyHostToDevice, S()));
   return b;
 }
 void out_buf(const Buf &b, size_t bytes = ~(size_t)0) {
-  if (b.host) GS_CUDA(cudaMemcpyAsync(b.host, b.dev, bytes < b.bytes ? bytes : b.bytes, cudaMemcpyDeviceToHost, 0));
+  if (b.host) GS_CUDA(cudaMemcpyAsync(b.host, b.dev, bytes < b.bytes ? bytes : b.bytes, cudaMemcpyDeviceToHost, S()));
 }
-void finish() { GS_CUDA(cudaStreamSynchronize(0)); }
+void finish() { GS_CUDA(cudaStreamSynchronize(S())); }
 
 }  // namespace
 
@@ -78,7 +105,7 @@ void gs_blur(struct gs_image dst, struct gs_image src, unsigned radius) {
   GSB_ASSERT(gs_ok(src) && gs_ok(dst) && dst.w == src.w && dst.h == src.h);  // reference :269
   const size_t n = (size_t)src.w * src.h;
   Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
-  GS_DO(gs_b200_blur_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, radius, 0));
+  GS_DO(gs_b200_blur_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, radius, S()));
   out_buf(d);
   finish();
 }
@@ -87,7 +114,7 @@ void gs_adaptive_threshold(struct gs_image dst, struct gs_image src, unsigned ra
   GSB_ASSERT(gs_ok(dst) && gs_ok(src) && dst.w == src.w && dst.h == src.h);  // reference :232
   const size_t n = (size_t)src.w * src.h;
   Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
-  GS_DO(gs_b200_adaptive_threshold_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, radius, c, 0));
+  GS_DO(gs_b200_adaptive_threshold_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, radius, c, S()));
   out_buf(d);
   finish();
 }
@@ -97,7 +124,7 @@ void gs_sobel(struct gs_image dst, struct gs_image src) {
   const size_t n = (size_t)src.w * src.h;
   // dst is copied in as well: its 1-px frame must keep the caller's bytes (reference :308-309)
   Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, true);
-  GS_DO(gs_b200_sobel_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  GS_DO(gs_b200_sobel_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
   out_buf(d);
   finish();
 }
@@ -106,8 +133,8 @@ static void morph(struct gs_image dst, struct gs_image src, int dilate) {
   GSB_ASSERT(gs_ok(dst) && gs_ok(src) && dst.w == src.w && dst.h == src.h);  // reference :287
   const size_t n = (size_t)src.w * src.h;
   Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
-  if (dilate) GS_DO(gs_b200_dilate_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
-  else GS_DO(gs_b200_erode_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  if (dilate) GS_DO(gs_b200_dilate_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
+  else GS_DO(gs_b200_erode_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
   out_buf(d);
   finish();
 }
@@ -118,7 +145,7 @@ void gs_resize(struct gs_image dst, struct gs_image src) {
   GSB_ASSERT(gs_ok(dst) && gs_ok(src));  // reference :172
   Buf s = in_buf(src.data, (size_t)src.w * src.h, gsb::WS_STAGE_A);
   Buf d = in_buf(dst.data, (size_t)dst.w * dst.h, gsb::WS_STAGE_B, false);
-  GS_DO(gs_b200_resize_batch((uint8_t *)d.dev, dst.w, dst.h, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  GS_DO(gs_b200_resize_batch((uint8_t *)d.dev, dst.w, dst.h, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
   out_buf(d);
   finish();
 }
@@ -127,7 +154,7 @@ void gs_downsample(struct gs_image dst, struct gs_image src) {
   GSB_ASSERT(gs_ok(src) && gs_ok(dst) && dst.w == src.w / 2 && dst.h == src.h / 2);  // reference :190
   Buf s = in_buf(src.data, (size_t)src.w * src.h, gsb::WS_STAGE_A);
   Buf d = in_buf(dst.data, (size_t)dst.w * dst.h, gsb::WS_STAGE_B, false);
-  GS_DO(gs_b200_downsample_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  GS_DO(gs_b200_downsample_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
   out_buf(d);
   finish();
 }
@@ -136,7 +163,7 @@ void gs_integral(struct gs_image src, unsigned *ii) {
   GSB_ASSERT(gs_ok(src) && ii);  // reference :745
   const size_t n = (size_t)src.w * src.h;
   Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(ii, n * 4, gsb::WS_STAGE_B, false);
-  GS_DO(gs_b200_integral_batch((uint32_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, 0));
+  GS_DO(gs_b200_integral_batch((uint32_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
   out_buf(d);
   finish();
 }
@@ -149,13 +176,13 @@ unsigned gs_fast(struct gs_image img, struct gs_image scoremap, struct gs_keypoi
   unsigned sw = gs_ok(scoremap) ? scoremap.w : 0, sh = gs_ok(scoremap) ? scoremap.h : 0;
   Buf m = in_buf(sw ? scoremap.data : nullptr, (size_t)sw * sh, gsb::WS_STAGE_B, true);
   Buf k = in_buf(kps, sizeof(struct gs_keypoint) * (size_t)nkps, gsb::WS_STAGE_C, false);
-  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!cnt) die("device workspace allocation", 1);
   uint8_t *mp = sw ? (uint8_t *)m.dev : (uint8_t *)cnt;  // never dereferenced when sw == 0
   GS_DO(gsb_fast_single((const uint8_t *)s.dev, img.w, img.h, mp, sw, sh, (struct gs_keypoint *)k.dev, cnt, nkps,
-                        threshold, 0));
+                        threshold, S()));
   unsigned n = 0;
-  GS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof(n), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof(n), cudaMemcpyDeviceToHost, S()));
   finish();
   out_buf(m);
   out_buf(k, sizeof(struct gs_keypoint) * (size_t)n);
@@ -166,11 +193,11 @@ unsigned gs_fast(struct gs_image img, struct gs_image scoremap, struct gs_keypoi
 float gs_compute_orientation(struct gs_image img, unsigned x, unsigned y, unsigned r) {
   GSB_ASSERT(gs_ok(img) && x >= r && y >= r && x < img.w - r && y < img.h - r);  // reference :609
   Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
-  float *out = static_cast<float *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  float *out = static_cast<float *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!out) die("device workspace allocation", 1);
-  GS_DO(gsb_orient_single((const uint8_t *)s.dev, img.w, x, y, r, out, 0));
+  GS_DO(gsb_orient_single((const uint8_t *)s.dev, img.w, x, y, r, out, S()));
   float a = 0;
-  GS_CUDA(cudaMemcpyAsync(&a, out, sizeof(a), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&a, out, sizeof(a), cudaMemcpyDeviceToHost, S()));
   finish();
   return a;
 }
@@ -179,7 +206,7 @@ void gs_brief_descriptor(struct gs_image img, struct gs_keypoint *kp) {
   GSB_ASSERT(gs_ok(img) && kp);  // reference :624
   Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
   Buf k = in_buf(kp, sizeof(struct gs_keypoint), gsb::WS_STAGE_C, true);
-  GS_DO(gsb_brief_single((const uint8_t *)s.dev, img.w, img.h, (struct gs_keypoint *)k.dev, 0));
+  GS_DO(gsb_brief_single((const uint8_t *)s.dev, img.w, img.h, (struct gs_keypoint *)k.dev, S()));
   out_buf(k);
   finish();
 }
@@ -190,12 +217,12 @@ unsigned gs_orb_extract(struct gs_image img, struct gs_keypoint *kps, unsigned n
   const size_t n = (size_t)img.w * img.h;
   Buf s = in_buf(img.data, n, gsb::WS_STAGE_A), m = in_buf(scoremap_buffer, n, gsb::WS_STAGE_B, true);
   Buf k = in_buf(kps, sizeof(struct gs_keypoint) * (size_t)nkps, gsb::WS_STAGE_C, false);
-  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!cnt) die("device workspace allocation", 1);
   GS_DO(gs_b200_orb_extract_batch((const uint8_t *)s.dev, img.w, img.h, 1, (uint8_t *)m.dev,
-                                  (struct gs_keypoint *)k.dev, cnt, nkps, threshold, 0));
+                                  (struct gs_keypoint *)k.dev, cnt, nkps, threshold, S()));
   unsigned c = 0;
-  GS_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&c, cnt, sizeof(c), cudaMemcpyDeviceToHost, S()));
   finish();
   out_buf(m);
   out_buf(k, sizeof(struct gs_keypoint) * (size_t)c);
@@ -220,7 +247,7 @@ void gs_filter(struct gs_image dst, struct gs_image src, struct gs_image kernel,
   }
   Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
   GS_DO(gs_b200_filter_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, kn ? kw_host : nullptr,
-                             kn ? kernel.w : 0, kn ? kernel.h : 0, norm, 0));
+                             kn ? kernel.w : 0, kn ? kernel.h : 0, norm, S()));
   out_buf(d);
   finish();
   if (kw_host != small) free(kw_host);
@@ -234,7 +261,7 @@ void gs_match_template(struct gs_image img, struct gs_image tmpl, struct gs_imag
   Buf t = in_buf(tmpl.data, (size_t)tmpl.w * tmpl.h, gsb::WS_STAGE_B);
   Buf r = in_buf(result.data, (size_t)result.w * result.h, gsb::WS_STAGE_C, false);
   GS_DO(gs_b200_match_template_batch((uint8_t *)r.dev, (const uint8_t *)s.dev, img.w, img.h, 1, (const uint8_t *)t.dev,
-                                     tmpl.w, tmpl.h, 0));
+                                     tmpl.w, tmpl.h, S()));
   out_buf(r);
   finish();
 }
@@ -242,11 +269,11 @@ void gs_match_template(struct gs_image img, struct gs_image tmpl, struct gs_imag
 struct gs_point gs_find_best_match(struct gs_image result) {
   GSB_ASSERT(gs_ok(result));  // reference :727
   Buf r = in_buf(result.data, (size_t)result.w * result.h, gsb::WS_STAGE_A);
-  struct gs_point *p = static_cast<struct gs_point *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  struct gs_point *p = static_cast<struct gs_point *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!p) die("device workspace allocation", 1);
-  GS_DO(gs_b200_find_best_match_batch(p, (const uint8_t *)r.dev, result.w, result.h, 1, 0));
+  GS_DO(gs_b200_find_best_match_batch(p, (const uint8_t *)r.dev, result.w, result.h, 1, S()));
   struct gs_point out = {0, 0};
-  GS_CUDA(cudaMemcpyAsync(&out, p, sizeof(out), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&out, p, sizeof(out), cudaMemcpyDeviceToHost, S()));
   finish();
   return out;
 }
@@ -255,7 +282,7 @@ void gs_histogram(struct gs_image img, unsigned hist[256]) {
   GSB_ASSERT(gs_ok(img) && hist != NULL);  // reference :200
   Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
   Buf d = in_buf(hist, sizeof(unsigned) * 256, gsb::WS_STAGE_B, false);
-  GS_DO(gs_b200_histogram_batch((unsigned *)d.dev, (const uint8_t *)s.dev, img.w, img.h, 1, 0));
+  GS_DO(gs_b200_histogram_batch((unsigned *)d.dev, (const uint8_t *)s.dev, img.w, img.h, 1, S()));
   out_buf(d);
   finish();
 }
@@ -263,11 +290,11 @@ void gs_histogram(struct gs_image img, unsigned hist[256]) {
 uint8_t gs_otsu_threshold(struct gs_image img) {
   GSB_ASSERT(gs_ok(img));  // reference :206
   Buf s = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
-  uint8_t *t = static_cast<uint8_t *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  uint8_t *t = static_cast<uint8_t *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!t) die("device workspace allocation", 1);
-  GS_DO(gs_b200_otsu_threshold_batch(t, nullptr, (const uint8_t *)s.dev, img.w, img.h, 1, 0));
+  GS_DO(gs_b200_otsu_threshold_batch(t, nullptr, (const uint8_t *)s.dev, img.w, img.h, 1, S()));
   uint8_t out = 0;
-  GS_CUDA(cudaMemcpyAsync(&out, t, 1, cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&out, t, 1, cudaMemcpyDeviceToHost, S()));
   finish();
   return out;
 }
@@ -275,7 +302,7 @@ uint8_t gs_otsu_threshold(struct gs_image img) {
 void gs_threshold(struct gs_image img, uint8_t thresh) {
   GSB_ASSERT(gs_ok(img));  // reference :227
   Buf d = in_buf(img.data, (size_t)img.w * img.h, gsb::WS_STAGE_A);
-  GS_DO(gs_b200_threshold_batch((uint8_t *)d.dev, img.w, img.h, 1, thresh, 0));
+  GS_DO(gs_b200_threshold_batch((uint8_t *)d.dev, img.w, img.h, 1, thresh, S()));
   out_buf(d);
   finish();
 }
@@ -287,15 +314,15 @@ unsigned gs_match_orb(const struct gs_keypoint *kps1, unsigned n1, const struct 
   Buf a = in_buf(kps1, sizeof(struct gs_keypoint) * (size_t)n1, gsb::WS_STAGE_A);
   Buf b = in_buf(n2 ? kps2 : nullptr, sizeof(struct gs_keypoint) * (size_t)n2, gsb::WS_STAGE_B);
   Buf m = in_buf(matches, sizeof(struct gs_match) * (size_t)max_matches, gsb::WS_STAGE_C, false);
-  unsigned *ctl = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  unsigned *ctl = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!ctl) die("device workspace allocation", 1);
   const unsigned hn[2] = {n1, n2};
-  GS_CUDA(cudaMemcpyAsync(ctl, hn, sizeof(hn), cudaMemcpyHostToDevice, 0));
+  GS_CUDA(cudaMemcpyAsync(ctl, hn, sizeof(hn), cudaMemcpyHostToDevice, S()));
   const struct gs_keypoint *k2 = n2 ? (const struct gs_keypoint *)b.dev : (const struct gs_keypoint *)a.dev;
   GS_DO(gs_b200_match_orb_batch((const struct gs_keypoint *)a.dev, ctl, n1, k2, ctl + 1, n2 ? n2 : 1, 1,
-                                (struct gs_match *)m.dev, ctl + 2, max_matches, max_distance, 0));
+                                (struct gs_match *)m.dev, ctl + 2, max_matches, max_distance, S()));
   unsigned c = 0;
-  GS_CUDA(cudaMemcpyAsync(&c, ctl + 2, sizeof(c), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&c, ctl + 2, sizeof(c), cudaMemcpyDeviceToHost, S()));
   finish();
   out_buf(m, sizeof(struct gs_match) * (size_t)c);
   finish();
@@ -308,11 +335,11 @@ unsigned gs_lbp_window(const struct gs_lbp_cascade *c, const unsigned *ii, unsig
   const int win_w = (int)((float)c->window_w * scale), win_h = (int)((float)c->window_h * scale);
   if (x + win_w > (int)iw || y + win_h > (int)ih) return 0;  // reference :793
   Buf t = in_buf(ii, (size_t)iw * ih * 4, gsb::WS_STAGE_A);
-  unsigned *out = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  unsigned *out = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!out) die("device workspace allocation", 1);
-  GS_DO(gsb_lbp_window_single(c, (const uint32_t *)t.dev, iw, ih, x, y, scale, out, 0));
+  GS_DO(gsb_lbp_window_single(c, (const uint32_t *)t.dev, iw, ih, x, y, scale, out, S()));
   unsigned r = 0;
-  GS_CUDA(cudaMemcpyAsync(&r, out, sizeof(r), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&r, out, sizeof(r), cudaMemcpyDeviceToHost, S()));
   finish();
   return r;
 }
@@ -324,12 +351,12 @@ unsigned gs_lbp_detect(const struct gs_lbp_cascade *c, const unsigned *ii, unsig
   if (max_rects == 0) return 0;
   Buf t = in_buf(ii, (size_t)iw * ih * 4, gsb::WS_STAGE_A);
   Buf r = in_buf(rects, sizeof(struct gs_rect) * (size_t)max_rects, gsb::WS_STAGE_C, false);
-  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(0, gsb::WS_STAGE_D, 256));
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
   if (!cnt) die("device workspace allocation", 1);
   GS_DO(gs_b200_lbp_detect_batch(c, (const uint32_t *)t.dev, iw, ih, 1, (struct gs_rect *)r.dev, cnt, max_rects,
-                                 scale_factor, min_scale, max_scale, step, 0));
+                                 scale_factor, min_scale, max_scale, step, S()));
   unsigned n = 0;
-  GS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof(n), cudaMemcpyDeviceToHost, 0));
+  GS_CUDA(cudaMemcpyAsync(&n, cnt, sizeof(n), cudaMemcpyDeviceToHost, S()));
   finish();
   out_buf(r, sizeof(struct gs_rect) * (size_t)n);
   finish();

@@ -21,7 +21,10 @@
 // The reference calls libm atan2f / sinf (grayskull.h:100-101); trig mode 0 evaluates glibc
 // 2.39's algorithms with IEEE-exact device arithmetic (see dev_sinf / dev_atan2f), so angles and
 // descriptors are bit-identical to the reference on the same box.
+#include <math.h>
 #include <string.h>
+
+#include <mutex>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -726,10 +729,26 @@ k_orb_brief(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__re
 // single-call forms of gs_compute_orientation / gs_brief_descriptor (one warp)
 __global__ void k_orient_one(const uint8_t *img, unsigned w, unsigned x, unsigned y, unsigned r, int trig_mode,
                              float *out) {
+  if (r > 15) {
+    // Beyond r = 15 the reference's float accumulators (:610-617) can exceed 2^24 and start rounding, so the
+    // sums are rebuilt the way the reference does: one thread, fp32 adds in its dy-outer / dx-inner order.
+    if (threadIdx.x == 0) {
+      float m01 = 0.0f, m10 = 0.0f;
+      const int ri = (int)r, r2 = (int)(r * r);
+      for (int dy = -ri; dy <= ri; dy++)
+        for (int dx = -ri; dx <= ri; dx++)
+          if (dx * dx + dy * dy <= r2) {
+            const int v = __ldg(img + (size_t)((int)y + dy) * w + ((int)x + dx));
+            m01 = __fadd_rn(m01, (float)(dy * v));
+            m10 = __fadd_rn(m10, (float)(dx * v));
+          }
+      *out = trig_mode ? atan2f(m01, m10) : dev_atan2f(m01, m10);
+    }
+    return;
+  }
   int m01, m10;
   disc_moments(img, w, (int)x, (int)y, (int)r, threadIdx.x, m01, m10);
-  // for r > 15 the reference's float accumulation may round; int32 moments stay exact while
-  // |moment| < 2^24, which holds for r <= 15 (the only radius the library itself uses)
+  // r <= 15: |moment| < 2^24, the reference's float sums are exact integers = these int32 sums
   const float a = orient_from_moments(m01, m10, trig_mode);
   if (threadIdx.x == 0) *out = a;
 }
@@ -737,6 +756,64 @@ __global__ void k_brief_one(const uint8_t *img, unsigned w, unsigned h, KpRec *k
   uint32_t desc[8];
   brief_words(img, w, h, (int)kp->w[0], (int)kp->w[1], __uint_as_float(kp->w[3]), threadIdx.x, trig_mode, desc);
   if (threadIdx.x < 8) kp->w[4 + threadIdx.x] = desc[threadIdx.x];
+}
+
+// ---- first-use libm self-check (trig mode 0) --------------------------------------------------------------
+// Trig mode 0 restates glibc 2.39's sinf / atan2f; the contract is "identical to the reference on the same box",
+// and the reference calls whatever libm that box has.  On first use the device routines are compared with THIS
+// host's libm on 8192 samples (the moment range atan2f sees, the angle range sinf sees); a host whose libm rounds
+// differently gets a one-time warning on stderr and gs_b200_trig_selfcheck() reports the mismatch count.
+constexpr int TRIG_CHECK_N = 4096;
+__global__ void k_trig_selfcheck(float *out) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)TRIG_CHECK_N) return;
+  // same sample formulas as the host side below (integers -> exact floats)
+  const int a = (int)((i * 2654435761u) >> 9) - (1 << 22), b = (int)((i * 40503u + 12345u) * 2246822519u >> 9) - (1 << 22);
+  out[i] = dev_atan2f((float)a, (float)b);
+  const float ang = __fmul_rn((float)((int)i - TRIG_CHECK_N / 2), 0.0023f);   // about [-4.7, 4.7]
+  out[TRIG_CHECK_N + i] = dev_sinf(ang);
+}
+static int g_trig_mismatch = -1;      // -1: not run yet
+static std::once_flag g_trig_once;
+static void trig_selfcheck_run() {
+  float *dev = nullptr;
+  static float host[2 * TRIG_CHECK_N];
+  cudaStream_t st = nullptr;
+  if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return;
+  if (cudaMalloc(&dev, sizeof(host)) == cudaSuccess) {
+    k_trig_selfcheck<<<(TRIG_CHECK_N + 255) / 256, 256, 0, st>>>(dev);
+    count_launches(1);
+    if (cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+      int bad = 0;
+      for (unsigned i = 0; i < (unsigned)TRIG_CHECK_N; i++) {
+        const int a = (int)((i * 2654435761u) >> 9) - (1 << 22), b = (int)((i * 40503u + 12345u) * 2246822519u >> 9) - (1 << 22);
+        volatile float fa = (float)a, fb = (float)b;
+        const float ra = atan2f(fa, fb);
+        volatile float ang = (float)((int)i - TRIG_CHECK_N / 2) * 0.0023f;
+        const float rs = sinf(ang);
+        bad += memcmp(&ra, &host[i], 4) != 0;
+        bad += memcmp(&rs, &host[TRIG_CHECK_N + i], 4) != 0;
+      }
+      g_trig_mismatch = bad;
+      if (bad)
+        fprintf(stderr,
+                "grayskull_b200: warning: this host's libm sinf/atan2f differ from the glibc-2.39 routines the "
+                "device restates (%d of %d samples); ORB angles/descriptors follow glibc 2.39 "
+                "(gs_b200_set_trig_mode(1) selects CUDA libdevice, angle within 1e-5)\n",
+                bad, 2 * TRIG_CHECK_N);
+    }
+    cudaFree(dev);
+  }
+  cudaStreamDestroy(st);
+}
+static void trig_selfcheck_once(cudaStream_t user) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(user, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return;   // never allocate / synchronise inside a graph capture; the check runs on a later call
+  }
+  std::call_once(g_trig_once, trig_selfcheck_run);
 }
 
 static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uint8_t *score, unsigned sw,
@@ -752,7 +829,9 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
   unsigned *masks = static_cast<unsigned *>(workspace(s, WS_FAST_B, sizeof(unsigned) * (size_t)rows * n * mw));
   if (!rowcount || !masks) return (int)cudaErrorMemoryAllocation;
   GSB_ASSERT(n <= 65535u && rows <= 0x7FFFFFFFu);
-  if (sw == w && sh == h && !force_generic()) {
+  // thresholds above 255 (the reference computes p + t / p - t in unsigned arithmetic, :496-498, which wraps for
+  // huge t) take the literal per-pixel kernel: the tiled kernel's 16-bit lane arithmetic assumes t <= 255
+  if (sw == w && sh == h && !force_generic() && threshold <= 255u) {
     dim3 grid((w + FT_W - 1) / FT_W, (h - 6 + FT_H - 1) / FT_H, n);
     GSB_ASSERT(grid.y <= 65535u);
     CUtensorMap tmap;
@@ -767,7 +846,7 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
     k_fast_score<<<grid, block, 0, s>>>(src, w, h, n, score, sw, sh, threshold);
   }
   GSB_LAUNCHED(1);
-  if (sw % 4 == 0 && reinterpret_cast<uintptr_t>(score) % 4 == 0 && sw >= w)
+  if (sw % 4 == 0 && reinterpret_cast<uintptr_t>(score) % 4 == 0 && sw >= w && sh >= h)   // word pre-test stays inside the map
     k_nms_mask<true><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
   else
     k_nms_mask<false><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
@@ -787,6 +866,10 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
 extern "C" {
 
 void gs_b200_set_trig_mode(int mode) { gsb::g_trig_mode = mode ? 1 : 0; }
+int gs_b200_trig_selfcheck(void) {
+  std::call_once(gsb::g_trig_once, gsb::trig_selfcheck_run);
+  return gsb::g_trig_mismatch;
+}
 
 int gs_b200_fast_batch(const uint8_t *src, unsigned w, unsigned h, unsigned n, uint8_t *scoremap,
                        struct gs_keypoint *kps, unsigned *counts, unsigned nkps, unsigned threshold,
@@ -816,6 +899,7 @@ int gs_b200_orb_extract_batch(const uint8_t *src, unsigned w, unsigned h, unsign
   const unsigned long long blocks = (warps + 7) / 8;
   GSB_ASSERT(blocks < 0x7FFFFFFFull);
   gsb::KpRec *kr = reinterpret_cast<gsb::KpRec *>(kps);
+  if (gsb::g_trig_mode == 0) gsb::trig_selfcheck_once(st);
   gsb::k_orb_moments<<<(unsigned)blocks, 256, 0, st>>>(src, w, h, kr, counts, nkps, n);
   gsb::k_orb_trig<<<(unsigned)((warps + 255) / 256), 256, 0, st>>>(kr, counts, nkps, n, gsb::g_trig_mode);
   if (w % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0 && !gsb::force_generic())
@@ -832,11 +916,13 @@ int gsb_fast_single(const uint8_t *src, unsigned w, unsigned h, uint8_t *score, 
   return gsb::fast_impl(src, w, h, 1, score, sw, sh, reinterpret_cast<gsb::KpRec *>(kps), count, nkps, threshold, s);
 }
 int gsb_orient_single(const uint8_t *img, unsigned w, unsigned x, unsigned y, unsigned r, float *out, cudaStream_t s) {
+  if (gsb::g_trig_mode == 0) gsb::trig_selfcheck_once(s);
   gsb::k_orient_one<<<1, 32, 0, s>>>(img, w, x, y, r, gsb::g_trig_mode, out);
   GSB_LAUNCHED(1);
   return 0;
 }
 int gsb_brief_single(const uint8_t *img, unsigned w, unsigned h, struct gs_keypoint *kp, cudaStream_t s) {
+  if (gsb::g_trig_mode == 0) gsb::trig_selfcheck_once(s);
   gsb::k_brief_one<<<1, 32, 0, s>>>(img, w, h, reinterpret_cast<gsb::KpRec *>(kp), gsb::g_trig_mode);
   GSB_LAUNCHED(1);
   return 0;

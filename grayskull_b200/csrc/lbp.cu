@@ -28,6 +28,8 @@
 //   k_lbp_count / k_row_scan : hits per 256-window block and their per-frame exclusive scan;
 //   k_lbp_emit   : rects written in the reference's (scale, y, x) order, truncated at max_rects
 //             (the reference stops scanning there, :819-823).
+#include <list>
+#include <memory>
 #include <mutex>
 #include <string.h>
 #include <vector>
@@ -633,13 +635,27 @@ struct PlanKey {
 };
 struct PlanEntry {
   PlanKey key;
-  void *blob;
+  void *blob = nullptr;
   DevCascade dc;
   std::vector<ScaleInfo> scales;
   std::vector<TilePlan> tiles;   // empty: k_lbp_scan3 not applicable
+  PlanEntry() = default;
+  PlanEntry(const PlanEntry &) = delete;
+  PlanEntry &operator=(const PlanEntry &) = delete;
+  // The device blob goes when the LAST holder lets go (the cache or a caller that is still enqueueing kernels on
+  // it); cudaFree waits for work already enqueued on the device, so kernels in flight keep valid tables.
+  ~PlanEntry() {
+    if (!blob) return;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != key.device) cudaSetDevice(key.device);
+    cudaFree(blob);
+    if (cur != key.device) cudaSetDevice(cur);
+  }
 };
+typedef std::shared_ptr<PlanEntry> PlanRef;
 static std::mutex g_plan_mutex;
-static std::vector<PlanEntry> g_plans;
+static std::list<PlanRef> g_plans;   // callers hold a PlanRef: eviction / another thread's insert never invalidates it
 
 static unsigned long long fnv(unsigned long long h, const void *p, size_t n) {
   const unsigned char *b = static_cast<const unsigned char *>(p);
@@ -692,16 +708,17 @@ static void build_scales(const struct gs_lbp_cascade *c, unsigned iw, unsigned i
   }
 }
 
-static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned ih, float sf, float mn, float mx,
-                           int step) {
+static PlanRef get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned ih, float sf, float mn, float mx,
+                        int step) {
   int dev = 0;
   cudaGetDevice(&dev);
   PlanKey key = {cascade_hash(c), iw, ih, sf, mn, mx, step, dev};
   std::lock_guard<std::mutex> lock(g_plan_mutex);
-  for (auto &e : g_plans)
-    if (e.key == key) return &e;
+  for (auto &r : g_plans)
+    if (r->key == key) return r;
 
-  PlanEntry e;
+  PlanRef ref = std::make_shared<PlanEntry>();
+  PlanEntry &e = *ref;
   e.key = key;
   std::vector<float> svals;
   build_scales(c, iw, ih, sf, mn, mx, step, svals, e.scales);
@@ -843,12 +860,9 @@ static PlanEntry *get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned
     e.dc.total_slots = (end + LBP_SLOTS_PER_CTA - 1) / LBP_SLOTS_PER_CTA * LBP_SLOTS_PER_CTA;
     e.dc.total_windows += (unsigned long long)s.nx * s.ny;
   }
-  if (g_plans.size() >= 16) {  // tiny cache: drop the oldest
-    cudaFree(g_plans.front().blob);
-    g_plans.erase(g_plans.begin());
-  }
-  g_plans.push_back(e);
-  return &g_plans.back();
+  if (g_plans.size() >= 16) g_plans.pop_front();   // tiny cache: drop the oldest (freed once nobody uses it)
+  g_plans.push_back(ref);
+  return ref;
 }
 
 }  // namespace gsb
@@ -873,7 +887,7 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   GSB_ASSERT(rects || max_rects == 0);
   if (n == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(s);
-  gsb::PlanEntry *p = gsb::get_plan(c, iw, ih, scale_factor, min_scale, max_scale, step);
+  gsb::PlanRef p = gsb::get_plan(c, iw, ih, scale_factor, min_scale, max_scale, step);
   if (!p) return gsb::record_error(cudaErrorMemoryAllocation, __FILE__, __LINE__);
   const gsb::DevCascade &dc = p->dc;
   if (dc.total_slots == 0 || max_rects == 0) {

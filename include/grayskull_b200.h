@@ -130,6 +130,11 @@ int gs_b200_orb_extract_batch(const uint8_t *src, unsigned w, unsigned h, unsign
  * 1:           CUDA libdevice atan2f/sinf (angle within 1e-5 of the reference, descriptor bits
  *              may differ where a rotated offset sits on an integer boundary). */
 void gs_b200_set_trig_mode(int mode);
+/* Mode 0 restates ONE libm (glibc 2.39); the reference calls the host's.  The first ORB call compares the device
+ * routines with this host's sinf/atan2f on 8192 samples and warns once on stderr if they differ.  This returns
+ * the number of differing samples (0 = this host's libm agrees; runs the check if it has not run yet; -1 = the
+ * check could not run). */
+int gs_b200_trig_selfcheck(void);
 
 /* gs_match_orb, reference grayskull.h:680-699, over npairs (set1, set2) pairs.  Pair p's sets start
  * at kps1 + p*stride1 / kps2 + p*stride2 and hold n1[p] / n2[p] keypoints (e.g. the output layout of

@@ -278,3 +278,26 @@ def check_next_golden(impl):
         assert ka.tobytes() == z[tag + "kps_a"].tobytes() and kb.tobytes() == z[tag + "kps_b"].tobytes(), tag
         m = impl.gs_match_orb(ka, kb, 300, 60.0)
         assert m.tobytes() == z[tag + "matches"].tobytes() and len(m) > 20, tag
+
+
+def oracle_chain(cascade_ptr, frame, **params):
+    """the C5 chain of grayskull_b200/pipeline.py (blur r=5 -> sobel -> orb_extract / integral + lbp_detect on
+    the sobel map) on one frame through the oracle restatement"""
+    import sys
+    O, L = oracle(), sys.modules[__name__]
+    p = dict(radius=5, nkps=1250, threshold=20, max_rects=4096, scale_factor=1.1, min_scale=1.0, max_scale=4.0, step=2)
+    p.update(params)
+    h, w = frame.shape
+    b = np.empty_like(frame)
+    O.gso_blur(L.ptr(b), L.ptr(frame), w, h, p["radius"])
+    s = np.zeros_like(frame)
+    O.gso_sobel(L.ptr(s), L.ptr(b), w, h)
+    k = np.zeros(p["nkps"], L.KP_DTYPE)
+    sm = np.zeros_like(frame)
+    nk = O.gso_orb_extract(L.ptr(s), w, h, L.ptr(k), p["nkps"], p["threshold"], L.ptr(sm))
+    t = np.empty(frame.shape, np.uint32)
+    O.gso_integral(L.ptr(s), w, h, L.ptr(t))
+    r = np.zeros(p["max_rects"], L.RECT_DTYPE)
+    nr = O.gso_lbp_detect(cascade_ptr, L.ptr(t), w, h, L.ptr(r), p["max_rects"], p["scale_factor"], p["min_scale"],
+                          p["max_scale"], p["step"])
+    return {"sobel": s, "kps": k[:nk], "rects": r[:nr]}

@@ -653,3 +653,135 @@ def test_c5_pipeline_composition(G, O, cas):
         t = o_integral(O, s)
         assert np.array_equal(ii[i].cpu().numpy().view(np.uint32), t)
         assert gr[i].tobytes() == o_detect(O, cas, t, 1000, 1.1, 1.0, 4.0, 2).tobytes()
+
+
+# ---- round 2: sharding over NCCL, re-entrancy, large-batch offsets, ADVICE cases ---------------------------
+def test_sharded_pipeline_nccl():
+    """one NCCL scatter of uint8 frames from rank 0, the C5 chain on every rank's shard, one
+    NCCL gather of sobel maps / keypoints / rects, compared frame by frame with the oracle chain on rank 0
+    (tests/shard_worker.py).  World size 2 when the box has two GPUs (gpurun --gpus 2), else the same code
+    path with a single rank (scatter / gather degenerate to local copies)."""
+    import subprocess
+    import sys
+    import torch
+    world = min(2, torch.cuda.device_count())
+    port = str(29600 + os.getpid() % 300)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", port, os.path.join(L.ROOT, "tests", "shard_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARD_OK world=%d" % world in r.stdout, r.stdout[-2000:]
+
+
+def test_single_image_api_is_reentrant(G, O):
+    """the reference's gs_* functions are re-entrant (SURVEY.md 8b "Threading"): eight host threads hammer the
+    drop-in API with different images and radii concurrently (ctypes releases the GIL inside the calls); every
+    result must equal the oracle's -- each thread stages through its own stream and arenas"""
+    import threading
+    rng = np.random.default_rng(5)
+    jobs = []
+    for i in range(8):
+        h, w = int(rng.integers(90, 400)), int(rng.integers(6, 40)) * 16
+        a = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        r = int(rng.integers(1, 8))
+        jobs.append((a, r, o_blur(O, a, r), o_sobel(O, a), o_integral(O, a)))
+    errs = []
+
+    def work(j):
+        a, r, wb, ws, wi = jobs[j]
+        try:
+            for _ in range(25):
+                d = np.empty_like(a); G.gs_blur(d, a, r)
+                s = np.zeros_like(a); G.gs_sobel(s, a)
+                ii = np.empty(a.shape, np.uint32); G.gs_integral(a, ii)
+                if not (np.array_equal(d, wb) and np.array_equal(s, ws) and np.array_equal(ii, wi)):
+                    errs.append(j)
+                    return
+        except Exception as e:   # noqa: BLE001
+            errs.append((j, repr(e)))
+
+    th = [threading.Thread(target=work, args=(j,)) for j in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+
+def test_last_frame_of_a_large_batch(G, O, cas):
+    """offset arithmetic past 4 GiB: frame 271 of a 272-frame 4096x4096 batch (byte offset 4.5 GB) for the
+    stencils, and the last frame of a 136-frame UHD integral batch (u32 table offset 4.5 GB)"""
+    import torch
+    n, h, w = 272, 4096, 4096
+    src = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+    f = np.random.default_rng(9).integers(0, 256, (h, w)).astype(np.uint8)
+    src[n - 1].copy_(dev(f))
+    blur = G.blur_batch(src, 5)
+    assert bool((blur[: n - 1] == 0).all())
+    b = blur[n - 1].cpu().numpy()
+    rng = np.random.default_rng(2)
+    _crop_check(b, f, lambda a: o_blur(O, a, 5), 5, rng)
+    del src
+    sob = G.sobel_batch(blur)
+    s = sob[n - 1].cpu().numpy()
+    for (x, y) in [(0, 0), (4096 - 200, 4096 - 200), (1777, 2000)]:
+        sub = np.ascontiguousarray(b[y:y + 200, x:x + 200])
+        assert np.array_equal(s[y + 1:y + 199, x + 1:x + 199], o_sobel(O, sub)[1:-1, 1:-1])
+    if hasattr(G, "blur_sobel_batch"):
+        src2 = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+        src2[n - 1].copy_(dev(f))
+        del sob
+        fs = G.blur_sobel_batch(src2, 5)
+        assert np.array_equal(fs[n - 1].cpu().numpy(), s)
+        del src2, fs
+    del blur
+    torch.cuda.empty_cache()
+    n4, h4, w4 = 136, 2160, 3840
+    f4 = L.natural_like(w4, h4, 31)
+    src4 = torch.zeros((n4, h4, w4), dtype=torch.uint8, device="cuda")
+    src4[n4 - 1].copy_(dev(f4))
+    ii = G.integral_batch(src4)
+    want_ii = o_integral(O, f4)
+    assert np.array_equal(ii[n4 - 1].cpu().numpy().view(np.uint32), want_ii)
+    rects, counts = G.lbp_detect_batch(cas, ii[n4 - 4:], 65536, 1.1, 1.0, 4.0, 2)
+    got = G.rects_to_numpy(rects, counts)
+    assert got[3].tobytes() == o_detect(O, cas, want_ii, 65536, 1.1, 1.0, 4.0, 2).tobytes()
+    assert len(got[0]) == 0
+
+
+def test_fast_huge_threshold_and_foreign_scoremap(G, O):
+    """thresholds above 255 wrap in the reference's unsigned arithmetic (:496-498) -- the result must not
+    depend on which kernel (tiled / per-pixel) runs; a score map shorter than the image must not be read past its end"""
+    a = L.natural_like(256, 96, 4)
+    for t in (256, 300, 2**31 + 5, 2**32 - 3, 2**32 - 200):
+        for force in (0, 1):
+            import grayskull_b200 as g
+            g.lib().gs_b200_force_generic(force)
+            try:
+                sm = np.zeros_like(a)
+                got = G.gs_fast(a, sm, 500, t)
+            finally:
+                g.lib().gs_b200_force_generic(0)
+            sm2 = np.zeros_like(a)
+            want = o_fast(O, a, sm2, 500, t)
+            assert got.tobytes() == want.tobytes() and np.array_equal(sm, sm2), (t, force)
+    sm = np.full((40, 256), 7, np.uint8)               # foreign size: fewer rows than the image
+    sm2 = sm.copy()
+    got = G.gs_fast(a, sm, 500, 20)
+    want = o_fast(O, a, sm2, 500, 20)
+    assert got.tobytes() == want.tobytes() and np.array_equal(sm, sm2)
+
+
+def test_orientation_large_radius(G):
+    """for r > 15 the reference's float moment sums round; the device follows the same fp32 order
+    (checked against the compiled reference through golden values generated by tools/make_golden.py)"""
+    z = np.load(os.path.join(GOLD, "round2_golden.npz"))
+    a = np.ascontiguousarray(z["orient_img"])
+    for (x, y, r), want in zip(z["orient_xyr"], z["orient_angle"]):
+        got = G.gs_compute_orientation(a, int(x), int(y), int(r))
+        assert np.float32(got).tobytes() == np.float32(want).tobytes(), (x, y, r, got, want)
+
+
+def test_trig_selfcheck_matches_this_libm():
+    """the device restates glibc 2.39's sinf / atan2f; on this image (glibc 2.39) the first-use self-check must
+    report zero differing samples"""
+    import grayskull_b200 as g
+    assert g.lib().gs_b200_trig_selfcheck() == 0

@@ -314,7 +314,7 @@ def test_shard_ranges_cover_every_frame_once():
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from grayskull_b200.shard import scatter_frames, gather_frames, shard_range
+from grayskull_b200.shard import scatter_frames, gather_frames, gather_many, shard_range
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank = dist.get_rank()
 n, h, w = 7, 5, 16
@@ -328,6 +328,17 @@ if rank == 0:
     assert torch.equal(out, 255 - (torch.arange(n * h * w, dtype=torch.int64) % 251).to(torch.uint8).reshape(n, h, w))
 else:
     assert out is None
+# several result tensors (maps, records, per-frame counts) in one group, into preallocated root buffers
+recs = torch.arange(lo, hi, dtype=torch.int32).reshape(-1, 1, 1).repeat(1, 3, 4) * 7
+cnts = torch.arange(lo, hi, dtype=torch.int32) + 100
+pre = [torch.zeros((n, h, w), dtype=torch.uint8), torch.zeros((n, 3, 4), dtype=torch.int32), torch.zeros((n,), dtype=torch.int32)] if rank == 0 else None
+res = gather_many([mine, recs, cnts], n, out=pre)
+if rank == 0:
+    assert res is pre and torch.equal(res[0], want_all := (torch.arange(n * h * w, dtype=torch.int64) % 251).to(torch.uint8).reshape(n, h, w))
+    assert torch.equal(res[1], torch.arange(n, dtype=torch.int32).reshape(-1, 1, 1).repeat(1, 3, 4) * 7)
+    assert torch.equal(res[2], torch.arange(n, dtype=torch.int32) + 100)
+else:
+    assert res is None
 dist.barrier(); dist.destroy_process_group(); print("ok", rank)
 '''
 
