@@ -43,6 +43,10 @@ MATCH_DTYPE = np.dtype([("idx1", "<u4"), ("idx2", "<u4"), ("distance", "<u4")])
 KP_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("response", "<u4"), ("angle", "<f4"),
                      ("descriptor", "<u4", (8,))])
 RECT_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("w", "<u4"), ("h", "<u4")])
+# struct gs_blob (reference grayskull.h:29-34): u16 label + 2 padding bytes, area, box, centroid = 32 bytes
+BLOB_DTYPE = np.dtype({"names": ["label", "area", "bx", "by", "bw", "bh", "cx", "cy"],
+                       "formats": ["<u2", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4"],
+                       "offsets": [0, 4, 8, 12, 16, 20, 24, 28], "itemsize": 32})
 assert KP_DTYPE.itemsize == 48 and RECT_DTYPE.itemsize == 16 and C.sizeof(Cascade) == 96
 
 
@@ -154,6 +158,12 @@ def ref():
         lib.gs_otsu_threshold.restype = C.c_uint8
         lib.gs_threshold.argtypes = [Image, C.c_uint8]
         lib.gs_threshold.restype = None
+        lib.gs_blobs.argtypes = [Image, C.c_void_p, C.c_void_p, C.c_uint]
+        lib.gs_blobs.restype = C.c_uint
+        lib.gs_blob_corners.argtypes = [Image, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gs_blob_corners.restype = None
+        lib.gs_perspective_correct.argtypes = [Image, Image, C.c_void_p]
+        lib.gs_perspective_correct.restype = None
         lib.ref_frontalface.restype = C.c_void_p
         lib.ref_sort_keypoints.argtypes = [C.c_void_p, C.c_uint]
         lib.ref_sort_keypoints.restype = None
@@ -216,6 +226,28 @@ def natural_like(w, h, seed=0):
     up = np.kron(small, np.ones((8, 8), np.float32))[:h, :w]
     noise = rng.normal(0, 12, size=(h, w)).astype(np.float32)
     return np.clip(up * 0.7 + noise + 30, 0, 255).astype(np.uint8)
+
+
+def blob_fields(b):
+    """the defined fields of a gs_blob array (the 2 padding bytes after `label` are not part of the contract)"""
+    return [tuple(int(b[k][i]) for k in BLOB_DTYPE.names) for i in range(len(b))]
+
+
+def binary_like(w, h, seed, density=0.5, smooth=3):
+    """0 / 255 image with blobs of assorted sizes (thresholded smooth noise) plus salt noise: many small
+    components, a few large ones, touching the borders"""
+    rng = np.random.default_rng(seed)
+    a = rng.random((h + 2 * smooth, w + 2 * smooth)).astype(np.float32)
+    k = 2 * smooth + 1
+    c = np.cumsum(np.cumsum(np.pad(a, ((1, 0), (1, 0))), 0), 1)
+    box = (c[k:, k:] - c[:-k, k:] - c[k:, :-k] + c[:-k, :-k]) / (k * k)
+    img = (box[:h, :w] > np.quantile(box, 1 - density)).astype(np.uint8) * 255
+    salt = rng.random((h, w))
+    img[salt < 0.02] = 255
+    img[salt > 0.98] = 0
+    img[rng.random((h, w)) < 0.01] = 130          # values just above / below the >= 128 foreground test
+    img[rng.random((h, w)) < 0.01] = 127
+    return np.ascontiguousarray(img)
 
 
 def desc_sets(rng, n1, n2, dup=0.3):

@@ -7,6 +7,9 @@ The GPU box has no /root/reference, so these small fixtures are committed.
   random_golden.npz   a handful of odd-sized random images (ragged widths, tiny sizes)
   next_golden.npz     the SURVEY.md 8(f) rows (gs_match_orb, histogram / Otsu / threshold, gs_filter,
                       gs_match_template / gs_find_best_match) on lena and two synthetic images
+  round2_golden.npz   radii beyond 7 (gs_blur / gs_adaptive_threshold r = 8..31, the reference Makefile's
+                      `blur 9` / `adaptive 15 5`), gs_compute_orientation for r > 15, and the 8(f) N4 row:
+                      gs_blobs (incl. running out of labels), gs_blob_corners, gs_perspective_correct
 """
 import hashlib
 import os
@@ -83,6 +86,64 @@ def run_next(R, a, tag, out, rng):
     return n
 
 
+def run_round2(R, lena, out):
+    rng = np.random.default_rng(2028)
+    # ---- large radii
+    imgs = {"lena": lena, "rag": rng.integers(0, 256, (75, 150)).astype(np.uint8), "w16": L.natural_like(208, 97, 5),
+            "tiny": rng.integers(0, 256, (9, 16)).astype(np.uint8)}
+    out["radius_tags"] = np.array(list(imgs))
+    out["radii"] = np.array([8, 9, 11, 15, 31])
+    for tag, a in imgs.items():
+        out["radius_img_" + tag] = a
+        for r in (8, 9, 11, 15, 31):
+            d = np.empty_like(a); R.gs_blur(L.img(d), L.img(a), r); out["blur%d_%s" % (r, tag)] = d
+            d = np.empty_like(a); R.gs_adaptive_threshold(L.img(d), L.img(a), r, 5 - r); out["adaptive%d_%s" % (r, tag)] = d
+    # ---- orientation beyond r = 15 (float accumulation rounds there)
+    big = np.clip(L.natural_like(400, 300, 11).astype(np.int32) + 90, 0, 255).astype(np.uint8)
+    out["orient_img"] = big
+    xyr, ang = [], []
+    for r in (3, 15, 16, 24, 40, 77, 120):
+        for _ in range(4):
+            x, y = int(rng.integers(r, 400 - r)), int(rng.integers(r, 300 - r))
+            xyr.append((x, y, r)); ang.append(R.gs_compute_orientation(L.img(big), x, y, r))
+    out["orient_xyr"], out["orient_angle"] = np.array(xyr), np.array(ang, np.float32)
+    # ---- blobs / corners / perspective
+    bimgs = {"b0": L.binary_like(64, 48, 1), "b1": L.binary_like(200, 120, 2, density=0.35), "b2": L.binary_like(131, 77, 3, density=0.6, smooth=1),
+             "b3": (lena > 110).astype(np.uint8) * 255, "b4": np.full((20, 33), 255, np.uint8), "b5": np.zeros((10, 10), np.uint8),
+             "b6": L.binary_like(512, 300, 4, density=0.45, smooth=5)}
+    snake = np.zeros((41, 64), np.uint8)           # comb / snake shapes: provisional labels merge late and in both directions
+    snake[::2, :] = 255; snake[1::4, 0] = 255; snake[3::4, -1] = 255
+    bimgs["b7"] = snake
+    comb = np.zeros((30, 61), np.uint8); comb[:, ::2] = 255; comb[-1, :] = 255
+    bimgs["b8"] = comb
+    out["blob_tags"] = np.array(list(bimgs))
+    for tag, a in bimgs.items():
+        out["blob_img_" + tag] = a
+        h, w = a.shape
+        for nb in (1000, 7, 1):
+            labels = np.full((h, w), 0xABCD, np.uint16)
+            blobs = np.zeros(nb, L.BLOB_DTYPE)
+            m = R.gs_blobs(L.img(a), L.ptr(labels), L.ptr(blobs), nb)
+            out["blob_%s_n%d_labels" % (tag, nb)] = labels
+            out["blob_%s_n%d_blobs" % (tag, nb)] = np.array(L.blob_fields(blobs[:m]), np.int64).reshape(m, 8)
+            if nb == 1000 and m:
+                cs = []
+                for i in range(min(m, 12)):
+                    c = np.zeros((4, 2), np.uint32)
+                    R.gs_blob_corners(L.img(a), L.ptr(labels), L.ptr(blobs[i:i + 1]), L.ptr(c)); cs.append(c)
+                out["blob_%s_corners" % tag] = np.array(cs)
+    src = L.natural_like(300, 220, 21)
+    out["persp_src"] = src
+    quads = [[(20, 30), (270, 10), (290, 200), (5, 180)], [(0, 0), (299, 0), (299, 219), (0, 219)], [(250, 200), (10, 190), (30, 15), (280, 40)],
+             [(100, 100), (100, 100), (100, 100), (100, 100)], [(0, 0), (1000, 5), (900, 700), (3, 400)]]
+    out["persp_quads"] = np.array(quads, np.uint32)
+    for qi, q in enumerate(quads):
+        for (dw, dh) in ((160, 100), (33, 47), (1, 1), (2, 5)):
+            d = np.empty((dh, dw), np.uint8)
+            c = np.array(q, np.uint32)
+            R.gs_perspective_correct(L.img(d), L.img(src), L.ptr(c)); out["persp_q%d_%dx%d" % (qi, dw, dh)] = d
+
+
 def main():
     R = L.ref()
     cas = R.ref_frontalface()
@@ -113,6 +174,10 @@ def main():
         n = run_next(R, a, tag, out, rng)
         print("%s %d matches, otsu %d, best %s" % (tag, n, int(out[tag + "otsu"]), out[tag + "tmatch_best"]))
     np.savez_compressed(os.path.join(gold, "next_golden.npz"), **out)
+    out = {}
+    run_round2(R, lena, out)
+    np.savez_compressed(os.path.join(gold, "round2_golden.npz"), **out)
+    print("round2: %d arrays" % len(out))
     print("wrote", gold)
 
 
