@@ -288,6 +288,153 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
   }
 }
 
+
+// ---- wide radii (8 <= r <= 120): radius-independent work, u32 window sums -------------------
+// The reference's own smoke runs use `blur 9` and `adaptive 15 5` (reference Makefile:17,20); the generic
+// kernel below costs (2r+1)^2 taps per pixel there.  This one costs the same ~14 instructions per pixel for
+// every radius.  Each WARP works alone (no CTA barrier) on a 256-column segment of a band of rows:
+//   vertical   : a lane keeps the column sums of its 8 columns over rows [y-r, y+r] as four u16x2 pair words
+//                ((2r+1) * 255 <= 65535 for r <= 128) and rolls them down the band, + entering row - leaving
+//                row, one IADD3 per word; rows come straight from global memory as coalesced 64-bit loads,
+//                prefetched one row ahead; out-of-image rows / columns read as 0 (a clipped tap's contribution);
+//   horizontal : inclusive prefix of the 256 column sums in u32 (8 local adds, a 5-step warp scan, 8 adds),
+//                written to a double-buffered 1 KB shared row; the window sum of column i is
+//                P[i+r] - P[i-r-1]: two LDS and a subtract.  A segment carries R8 = roundup(r, 8) halo
+//                columns on both sides, so 256 - 2*R8 outputs per warp-row;
+//   division   : interior pixels (count = (2r+1)^2, r <= 63) use the exact fma_rd trick of the small-radius
+//                kernel with m = ceil(2^k / count), k = 23 + floor(log2 count) (host-verified for every sum
+//                that can occur, box_wide_magic_ok); clipped counts and r > 63 take
+//                floor(fdiv_rn(S, count)), which is exact for count < 2^17 and quotients <= 255 (the distance of
+//                S/count to the next integer is >= 1/count > half an ulp).
+template <bool ADAPTIVE, bool ALIGNED>
+__global__ void __launch_bounds__(128)
+k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int h, int r, int R8, int BH,
+           int strips, int cparam, float minv, int fast_ok) {
+  __shared__ __align__(16) uint32_t sp_all[4][2][264];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = (int)blockIdx.x * 4 + warp;
+  if (strip >= strips) return;                                  // warp-uniform; no CTA barriers below
+  const int outw = 256 - 2 * R8;
+  const int xs = strip * outw - R8;                             // image column of segment column 0 (multiple of 8)
+  const int x0 = xs + 8 * lane;
+  const int yb = (int)blockIdx.y * BH, ye = min(h, yb + BH);
+  const uint8_t *frame = src + (size_t)blockIdx.z * w * h;
+  uint8_t *out = dst + (size_t)blockIdx.z * w * h;
+  const bool lane_in = ALIGNED ? (x0 >= 0 && x0 < w) : (x0 + 7 >= 0 && x0 < w);
+  const bool out_lane = 8 * lane >= R8 && 8 * lane + 8 <= 256 - R8 && x0 < w && x0 + 7 >= 0;
+  const int FULL = 2 * r + 1;
+  // all 8 pixels of this lane have the full (2r+1)-column window inside the image
+  const bool cols_full = x0 - r >= 0 && x0 + 7 + r <= w - 1;
+
+  auto ld = [&](int y) -> uint2 {
+    if (!lane_in || y < 0 || y >= h) return make_uint2(0u, 0u);
+    const uint8_t *p = frame + (size_t)y * w + x0;
+    if (ALIGNED) return __ldg(reinterpret_cast<const uint2 *>(p));
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (x0 + k >= 0 && x0 + k < w) a |= (uint32_t)__ldg(p + k) << (8 * k);
+      if (x0 + 4 + k >= 0 && x0 + 4 + k < w) b |= (uint32_t)__ldg(p + 4 + k) << (8 * k);
+    }
+    return make_uint2(a, b);
+  };
+
+  uint32_t S[4] = {0, 0, 0, 0};
+#pragma unroll 4
+  for (int yy = yb - r; yy <= yb + r; yy++) {
+    uint32_t e[4];
+    unpack_pairs(ld(yy), e);
+#pragma unroll
+    for (int k = 0; k < 4; k++) S[k] += e[k];
+  }
+  uint2 en = ld(yb + r + 1), lv = ld(yb - r), cen = make_uint2(0u, 0u);
+  if (ADAPTIVE) cen = ld(yb);
+  uint32_t *sp0 = sp_all[warp][0], *sp1 = sp_all[warp][1];
+
+  for (int y = yb; y < ye; y++) {
+    const uint2 en2 = ld(y + r + 2), lv2 = ld(y + 1 - r);
+    uint2 cen2 = make_uint2(0u, 0u);
+    if (ADAPTIVE) cen2 = ld(y + 1);
+    // ---- horizontal prefix of the column sums (u32)
+    uint32_t p[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p[2 * k] = S[k] & 0xFFFFu, p[2 * k + 1] = S[k] >> 16;
+#pragma unroll
+    for (int k = 1; k < 8; k++) p[k] += p[k - 1];
+    uint32_t incl = p[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - p[7];
+    uint32_t *sp = ((y - yb) & 1) ? sp1 : sp0;
+    uint4 *spw = reinterpret_cast<uint4 *>(sp + 4 + 8 * lane);   // P(i) lives at sp[i + 4]; sp[3] = P(-1)
+    spw[0] = make_uint4(p[0] + excl, p[1] + excl, p[2] + excl, p[3] + excl);
+    spw[1] = make_uint4(p[4] + excl, p[5] + excl, p[6] + excl, p[7] + excl);
+    if (lane == 0) sp[3] = 0u;                                    // P(-1) = 0
+    __syncwarp();
+    if (out_lane) {
+      const int i0 = 8 * lane;
+      uint32_t W[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) W[k] = sp[4 + i0 + k + r] - sp[3 + i0 + k - r];
+      const int ch = min(y + r, h - 1) - max(y - r, 0) + 1;
+      uint32_t q[8];
+      if (fast_ok && cols_full && ch == FULL) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = __float_as_uint(__fmaf_rd((float)W[k], minv, 8388608.0f)) & 0xFFu;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int x = x0 + k;
+          const int cw = min(x + r, w - 1) - max(x - r, 0) + 1;
+          q[k] = __float2uint_rd(__fdiv_rn((float)W[k], (float)(cw * ch)));
+        }
+      }
+      if (ADAPTIVE) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int sv = (int)(((k < 4 ? cen.x : cen.y) >> (8 * (k & 3))) & 0xFFu);
+          q[k] = sv > (int)(q[k] - (unsigned)cparam) ? 255u : 0u;      // reference :244-245
+        }
+      }
+      uint2 o;
+      o.x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+      o.y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
+      uint8_t *qo = out + (size_t)y * w + x0;
+      if (ALIGNED) {
+        st_cs_u2(qo, o);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (x0 + k >= 0 && x0 + k < w) qo[k] = (uint8_t)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
+      }
+    }
+    // ---- roll the column sums down one row
+    uint32_t e[4], l[4];
+    unpack_pairs(en, e);
+    unpack_pairs(lv, l);
+#pragma unroll
+    for (int k = 0; k < 4; k++) S[k] = S[k] + e[k] - l[k];
+    en = en2, lv = lv2, cen = cen2;
+  }
+}
+
+// k, m for the exact interior division of k_box_wide: floor(S * m / 2^k) == S / count for every S <= 255 * count
+static bool box_wide_magic(unsigned count, float *minv) {
+  int lg = 0;
+  while ((2u << lg) <= count) lg++;
+  const int k = 23 + lg;
+  const unsigned long long m = ((1ull << k) + count - 1) / count;
+  if (m >= (1ull << 24)) return false;
+  // S*m/2^k = S/count + S*e/(count*2^k), e = m*count - 2^k: exact iff the excess stays below 1/count for S <= 255*count
+  const unsigned long long e = m * count - (1ull << k);
+  if (255ull * count * e >= (1ull << k)) return false;
+  *minv = ldexpf((float)m, -k);
+  return true;
+}
+
 // ---- generic: any radius, width, alignment; one thread per pixel ----------------------------
 template <bool ADAPTIVE>
 __global__ void k_box_generic(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, unsigned w,
@@ -343,6 +490,30 @@ static int launch_box(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, 
       case 6: return launch_box_r<6, ADAPTIVE>(tmap, dst, w, h, n, cparam, s);
       default: return launch_box_r<7, ADAPTIVE>(tmap, dst, w, h, n, cparam, s);
     }
+  }
+  if (r >= 1 && r <= 120 && !force_generic() && n <= 65535u && w < (1u << 30) && h < (1u << 30)) {
+    // radius-independent path: warp-autonomous 256-column segments, u32 window sums (k_box_wide)
+    const int R8 = (int)((r + 7) / 8 * 8), outw = 256 - 2 * R8;
+    const int strips = (int)((w + outw - 1) / outw);
+    // enough warps to fill 148 SMs, bands no shorter than 4r rows (vertical halo re-reads <= 1/3)
+    const long long want = 148ll * 24;
+    long long bands = (want + (long long)strips * n - 1) / ((long long)strips * n);
+    const long long max_bands = ((long long)h + (4 * (long long)r > 32 ? 4 * (long long)r : 32) - 1) / (4 * (long long)r > 32 ? 4 * (long long)r : 32);
+    if (bands > max_bands) bands = max_bands;
+    if (bands < 1) bands = 1;
+    int BH = (int)((h + bands - 1) / bands);
+    const unsigned gy = (h + BH - 1) / BH;
+    GSB_ASSERT(gy <= 65535u);
+    float minv = 0.0f;
+    const int fast_ok = (r <= 63 && box_wide_magic((2 * r + 1) * (2 * r + 1), &minv)) ? 1 : 0;
+    const bool aligned = w % 8 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0 && reinterpret_cast<uintptr_t>(dst) % 8 == 0;
+    dim3 grid((strips + 3) / 4, gy, n);
+    if (aligned)
+      k_box_wide<ADAPTIVE, true><<<grid, 128, 0, s>>>(dst, src, (int)w, (int)h, (int)r, R8, BH, strips, cparam, minv, fast_ok);
+    else
+      k_box_wide<ADAPTIVE, false><<<grid, 128, 0, s>>>(dst, src, (int)w, (int)h, (int)r, R8, BH, strips, cparam, minv, fast_ok);
+    GSB_LAUNCHED(1);
+    return 0;
   }
   dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8, n < 65535u ? n : 65535u);
   k_box_generic<ADAPTIVE><<<grid, block, 0, s>>>(dst, src, w, h, n, r, cparam);

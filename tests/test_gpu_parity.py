@@ -785,3 +785,40 @@ def test_trig_selfcheck_matches_this_libm():
     report zero differing samples"""
     import grayskull_b200 as g
     assert g.lib().gs_b200_trig_selfcheck() == 0
+
+
+WIDE_SHAPES = [(256, 128), (272, 140), (640, 480), (100, 37), (612, 90), (17, 1), (1, 1), (1024, 300), (2048, 67)]
+
+
+def test_wide_radius_box_vs_oracle_and_reference_goldens(G, O):
+    """radii beyond 7 (the reference Makefile's `blur 9`, `adaptive 15 5`) run the
+    radius-independent kernel (k_box_wide); r > 120 falls back to the per-pixel kernel.  Against the oracle on
+    aligned, ragged and tiny shapes, band / strip seams included, and against reference-generated goldens."""
+    rng = np.random.default_rng(11)
+    for (w, h) in WIDE_SHAPES:
+        frames = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint8), L.natural_like(w, h, 8),
+                           np.full((h, w), 255, np.uint8)])
+        src = dev(frames)
+        for r in (8, 9, 12, 15, 16, 31, 63, 64, 100, 120, 121, 300):
+            if r > 31 and w * h > 200000:
+                continue                       # the oracle's cost grows with r
+            gb = G.blur_batch(src, r).cpu().numpy()
+            c = int(rng.integers(-60, 60))
+            ga = G.adaptive_threshold_batch(src, r, c).cpu().numpy()
+            for i in range(3):
+                assert np.array_equal(gb[i], o_blur(O, frames[i], r)), ("blur", w, h, r, i)
+                assert np.array_equal(ga[i], o_adaptive(O, frames[i], r, c)), ("adaptive", w, h, r, c, i)
+    z = np.load(os.path.join(GOLD, "round2_golden.npz"))
+    for tag in z["radius_tags"]:
+        a = np.ascontiguousarray(z["radius_img_" + str(tag)])
+        for r in z["radii"]:
+            r = int(r)
+            d = np.empty_like(a); G.gs_blur(d, a, r)
+            assert np.array_equal(d, z["blur%d_%s" % (r, tag)]), ("golden blur", tag, r)
+            d = np.empty_like(a); G.gs_adaptive_threshold(d, a, r, 5 - r)
+            assert np.array_equal(d, z["adaptive%d_%s" % (r, tag)]), ("golden adaptive", tag, r)
+    # a tall frame: several row bands per strip (band seams), full-size width
+    f = L.natural_like(4096, 1500, 12)
+    got = G.blur_batch(dev(f[None]), 15)[0].cpu().numpy()
+    rng2 = np.random.default_rng(3)
+    _crop_check(got, f, lambda a: o_blur(O, a, 15), 15, rng2)

@@ -177,6 +177,33 @@ def test_box_division_constants_are_exact():
         assert (S.max() * m) / 2 ** 24 < 2 ** 23
 
 
+def test_wide_box_division_is_exact():
+    """box.cu k_box_wide: interior quotients come from fma_rd(float(S), m * 2^-k, 2^23) with k = 23 + floor(log2 count),
+    m = ceil(2^k / count): m must be an exact float (< 2^24) and floor(S*m / 2^k) == S // count for every window sum
+    S <= 255 * count, count = (2r+1)^2, r = 8..63 (the radii box_wide_magic accepts); clipped counts use
+    floor(fdiv_rn(S, count)), exact because S/count is at least 1/count > half an ulp away from the next integer."""
+    for r in range(8, 64):
+        count = (2 * r + 1) ** 2
+        k = 23 + int(np.floor(np.log2(count)))
+        m = ((1 << k) + count - 1) // count
+        assert m < 1 << 24, r
+        e = m * count - (1 << k)
+        assert 255 * count * e < 1 << k, r                       # the host-side acceptance test of box_wide_magic
+        step = 1 if r <= 20 else 7                               # every S for the common radii, a stride beyond
+        S = np.arange(0, 255 * count + 1, step, dtype=np.int64)
+        S = np.concatenate([S, np.arange(count - 1, 255 * count + 1, count), np.arange(0, 255 * count + 1, count)])
+        assert np.array_equal([int(v) for v in (S.astype(object) * m) >> k] if r > 50 else (S * m) >> k, S // count), r
+        assert float(S.max()) * m / 2.0 ** k < 2 ** 23
+    # the fdiv path: worst cases q*d + (d - 1) for d up to 241^2 (r = 120), in float32 arithmetic
+    for d in (289, 961, 16129, 16641, 58081, 65025, 241 * 241):
+        q = np.arange(0, 256, dtype=np.int64)
+        for f in (d - 1, d - 2, 0, 1):
+            S = q * d + f
+            S = S[S < 1 << 24]
+            got = np.floor(S.astype(np.float32) / np.float32(d)).astype(np.int64)
+            assert np.array_equal(got, S // d), (d, f)
+
+
 def test_filter_magic_division_is_exact():
     """filter.cu fast path: for norm >= 2, min(255, umulhi((u32)sum, floor(2^32/norm)+1)) equals the reference's
     `sum = sum / norm` (int converted to unsigned, quotient back to int, clamp 0..255) for every sum the host check
