@@ -8,4 +8,4 @@ This package is the thin host-side mirror used by the tests and bench.py:
     grayskull_b200.api          gs_* on numpy arrays (host pointers), *_batch on torch CUDA tensors
     grayskull_b200.shard        frame-batch sharding across ranks (torch.distributed)
 """
-from ._lib import lib, Image, Keypoint, Rect, Cascade, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE, load_cascade  # noqa: F401
+from ._lib import lib, Image, Keypoint, Rect, Cascade, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE, BLOB_DTYPE, load_cascade  # noqa: F401

@@ -42,6 +42,10 @@ KP_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("response", "<u4"), ("angle", 
                      ("descriptor", "<u4", (8,))])
 RECT_DTYPE = np.dtype([("x", "<u4"), ("y", "<u4"), ("w", "<u4"), ("h", "<u4")])
 MATCH_DTYPE = np.dtype([("idx1", "<u4"), ("idx2", "<u4"), ("distance", "<u4")])
+# struct gs_blob (reference grayskull.h:29-34): u16 label + 2 padding bytes, area, box, centroid
+BLOB_DTYPE = np.dtype({"names": ["label", "area", "bx", "by", "bw", "bh", "cx", "cy"],
+                       "formats": ["<u2", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4", "<u4"],
+                       "offsets": [0, 4, 8, 12, 16, 20, 24, 28], "itemsize": 32})
 
 _u, _i, _f, _p, _sz = C.c_uint, C.c_int, C.c_float, C.c_void_p, C.c_size_t
 
@@ -67,6 +71,9 @@ SIGNATURES = {
     "gs_histogram": (None, [Image, _p]),
     "gs_otsu_threshold": (C.c_uint8, [Image]),
     "gs_threshold": (None, [Image, C.c_uint8]),
+    "gs_blobs": (_u, [Image, _p, _p, _u]),
+    "gs_blob_corners": (None, [Image, _p, _p, _p]),
+    "gs_perspective_correct": (None, [Image, Image, _p]),
     "gs_lbp_window": (_u, [_p, _p, _u, _u, _i, _i, _f]),
     "gs_lbp_detect": (_u, [_p, _p, _u, _u, _p, _u, _f, _f, _f, _i]),
     # include/grayskull_b200.h
@@ -90,11 +97,15 @@ SIGNATURES = {
     "gs_b200_blur_batch": (_i, [_p, _p, _u, _u, _u, _u, _p]),
     "gs_b200_adaptive_threshold_batch": (_i, [_p, _p, _u, _u, _u, _u, _i, _p]),
     "gs_b200_sobel_batch": (_i, [_p, _p, _u, _u, _u, _p]),
+    "gs_b200_blur_sobel_batch": (_i, [_p, _p, _u, _u, _u, _u, _p]),
     "gs_b200_erode_batch": (_i, [_p, _p, _u, _u, _u, _p]),
     "gs_b200_dilate_batch": (_i, [_p, _p, _u, _u, _u, _p]),
     "gs_b200_resize_batch": (_i, [_p, _u, _u, _p, _u, _u, _u, _p]),
     "gs_b200_downsample_batch": (_i, [_p, _p, _u, _u, _u, _p]),
     "gs_b200_integral_batch": (_i, [_p, _p, _u, _u, _u, _p]),
+    "gs_b200_blobs_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _p]),
+    "gs_b200_blob_corners": (_i, [_p, _u, _u, _p, _p, _p, _p]),
+    "gs_b200_perspective_correct_batch": (_i, [_p, _u, _u, _p, _u, _u, _u, _p, _i, _p]),
     "gs_b200_fast_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_orb_extract_batch": (_i, [_p, _u, _u, _u, _p, _p, _p, _u, _u, _p]),
     "gs_b200_set_trig_mode": (None, [_i]),

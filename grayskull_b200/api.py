@@ -11,7 +11,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import lib, check, Image, Point, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE
+from ._lib import lib, check, Image, Point, KP_DTYPE, RECT_DTYPE, MATCH_DTYPE, BLOB_DTYPE
 
 
 def _img(a):
@@ -121,6 +121,27 @@ def gs_match_orb(kps1, kps2, max_matches, max_distance):
     return m[:n]
 
 
+def gs_blobs(img, nblobs):
+    """-> (labels (h, w) uint16, blobs BLOB_DTYPE[m])"""
+    labels = np.zeros(img.shape, np.uint16)
+    blobs = np.zeros(max(nblobs, 1), BLOB_DTYPE)
+    m = lib().gs_blobs(_img(img), _vp(labels), _vp(blobs), nblobs)
+    return labels, blobs[:m]
+
+
+def gs_blob_corners(img, labels, blob):
+    """blob: 1-element BLOB_DTYPE array -> (4, 2) uint32 corners tl, tr, br, bl"""
+    c = np.zeros((4, 2), np.uint32)
+    lib().gs_blob_corners(_img(img), _vp(labels), _vp(blob), _vp(c))
+    return c
+
+
+def gs_perspective_correct(dst, src, corners):
+    c = np.ascontiguousarray(corners, np.uint32)
+    lib().gs_perspective_correct(_img(dst), _img(src), _vp(c))
+    return dst
+
+
 def gs_lbp_window(cascade, ii, x, y, scale):
     return lib().gs_lbp_window(cascade.ptr, _vp(ii), ii.shape[1], ii.shape[0], x, y, scale)
 
@@ -170,6 +191,16 @@ def sobel_batch(src, out=None):
     n, h, w = _chk_frames(src)
     out = torch.zeros_like(src) if out is None else out
     check(lib().gs_b200_sobel_batch(_p(out), _p(src), w, h, n, _stream()), "sobel_batch")
+    return out
+
+
+def blur_sobel_batch(src, radius, out=None):
+    """gs_blur(radius) -> gs_sobel in one pass (no blurred intermediate in HBM); `out` keeps its 1-px frame,
+    a fresh output is zero-filled like gs_alloc"""
+    import torch
+    n, h, w = _chk_frames(src)
+    out = torch.zeros_like(src) if out is None else out
+    check(lib().gs_b200_blur_sobel_batch(_p(out), _p(src), w, h, n, radius, _stream()), "blur_sobel_batch")
     return out
 
 
@@ -311,6 +342,31 @@ def match_orb_batch(kps1, counts1, kps2, counts2, max_matches, max_distance):
     check(lib().gs_b200_match_orb_batch(_p(kps1), _p(counts1), s1, _p(kps2), _p(counts2), s2, npairs, _p(matches),
                                         _p(counts), max_matches, max_distance, _stream()), "match_orb_batch")
     return matches, counts
+
+
+def blobs_batch(src, nblobs):
+    """(n, h, w) uint8 -> (labels (n, h, w) int16 storage of the uint16 labels, blobs (n, nblobs, 8) int32 words, counts (n,))"""
+    import torch
+    n, h, w = _chk_frames(src)
+    labels = torch.empty((n, h, w), dtype=torch.int16, device=src.device)
+    blobs = torch.zeros((n, nblobs, 8), dtype=torch.int32, device=src.device)
+    counts = torch.empty((n,), dtype=torch.int32, device=src.device)
+    check(lib().gs_b200_blobs_batch(_p(src), w, h, n, _p(labels), _p(blobs), _p(counts), nblobs, _stream()), "blobs_batch")
+    return labels, blobs, counts
+
+
+def perspective_correct_batch(src, dw, dh, corners, out=None):
+    """corners: (4, 2) numpy (one quad for every frame, host) or an (n, 4, 2) int32 CUDA tensor (per frame)"""
+    import torch
+    n, h, w = _chk_frames(src)
+    out = torch.empty((n, dh, dw), dtype=torch.uint8, device=src.device) if out is None else out
+    if isinstance(corners, np.ndarray):
+        c = np.ascontiguousarray(corners, np.uint32)
+        check(lib().gs_b200_perspective_correct_batch(_p(out), dw, dh, _p(src), w, h, n, _vp(c), 0, _stream()), "perspective")
+    else:
+        assert corners.is_cuda and corners.dtype == torch.int32 and corners.is_contiguous() and corners.shape == (n, 4, 2)
+        check(lib().gs_b200_perspective_correct_batch(_p(out), dw, dh, _p(src), w, h, n, _p(corners), 1, _stream()), "perspective")
+    return out
 
 
 def lbp_detect_batch(cascade, ii, max_rects, scale_factor, min_scale, max_scale, step):

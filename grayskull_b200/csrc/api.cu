@@ -329,6 +329,56 @@ unsigned gs_match_orb(const struct gs_keypoint *kps1, unsigned n1, const struct 
   return c;
 }
 
+unsigned gs_blobs(struct gs_image img, gs_label *labels, struct gs_blob *blobs, unsigned nblobs) {
+  GSB_ASSERT(gs_ok(img) && labels != NULL && blobs != NULL && nblobs > 0);  // reference :335
+  const size_t n = (size_t)img.w * img.h;
+  Buf s = in_buf(img.data, n, gsb::WS_STAGE_A), l = in_buf(labels, n * sizeof(gs_label), gsb::WS_STAGE_B, false);
+  Buf b = in_buf(blobs, sizeof(struct gs_blob) * (size_t)nblobs, gsb::WS_STAGE_C, false);
+  unsigned *cnt = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
+  if (!cnt) die("device workspace allocation", 1);
+  GS_DO(gs_b200_blobs_batch((const uint8_t *)s.dev, img.w, img.h, 1, (gs_label *)l.dev, (struct gs_blob *)b.dev, cnt, nblobs,
+                            S()));
+  unsigned m = 0;
+  GS_CUDA(cudaMemcpyAsync(&m, cnt, sizeof(m), cudaMemcpyDeviceToHost, S()));
+  finish();
+  out_buf(l);
+  out_buf(b, sizeof(struct gs_blob) * (size_t)m);
+  finish();
+  return m;
+}
+
+void gs_blob_corners(struct gs_image img, gs_label *labels, struct gs_blob *b, struct gs_point c[4]) {
+  GSB_ASSERT(gs_ok(img) && b && labels);  // reference :409
+  const size_t n = (size_t)img.w * img.h;
+  Buf s = in_buf(img.data, n, gsb::WS_STAGE_A), l = in_buf(labels, n * sizeof(gs_label), gsb::WS_STAGE_B);
+  Buf bb = in_buf(b, sizeof(struct gs_blob), gsb::WS_STAGE_C);
+  unsigned *out = static_cast<unsigned *>(gsb::workspace(S(), gsb::WS_STAGE_D, 256));
+  if (!out) die("device workspace allocation", 1);
+  GS_DO(gs_b200_blob_corners((const uint8_t *)s.dev, img.w, img.h, (const gs_label *)l.dev, (const struct gs_blob *)bb.dev,
+                             (struct gs_point *)out, S()));
+  if (on_device(c)) {
+    GS_CUDA(cudaMemcpyAsync(c, out, 4 * sizeof(struct gs_point), cudaMemcpyDeviceToDevice, S()));
+  } else {
+    GS_CUDA(cudaMemcpyAsync(c, out, 4 * sizeof(struct gs_point), cudaMemcpyDeviceToHost, S()));
+  }
+  finish();
+}
+
+void gs_perspective_correct(struct gs_image dst, struct gs_image src, struct gs_point c[4]) {
+  GSB_ASSERT(gs_ok(dst) && gs_ok(src));  // reference :424
+  struct gs_point hc[4];
+  if (on_device(c)) {
+    GS_CUDA(cudaMemcpy(hc, c, sizeof(hc), cudaMemcpyDeviceToHost));
+  } else {
+    memcpy(hc, c, sizeof(hc));
+  }
+  Buf s = in_buf(src.data, (size_t)src.w * src.h, gsb::WS_STAGE_A);
+  Buf d = in_buf(dst.data, (size_t)dst.w * dst.h, gsb::WS_STAGE_B, false);
+  GS_DO(gs_b200_perspective_correct_batch((uint8_t *)d.dev, dst.w, dst.h, (const uint8_t *)s.dev, src.w, src.h, 1, hc, 0, S()));
+  out_buf(d);
+  finish();
+}
+
 unsigned gs_lbp_window(const struct gs_lbp_cascade *c, const unsigned *ii, unsigned iw, unsigned ih, int x, int y,
                        float scale) {
   GSB_ASSERT(c && ii);

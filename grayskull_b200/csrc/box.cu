@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "pairs.cuh"
 
 namespace gsb {
 
@@ -289,6 +290,136 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
 }
 
 
+
+// ---- fused gs_blur(r) -> gs_sobel: the blurred frame never goes to HBM ------------------------
+// gs_b200_blur_sobel_batch(dst, src, r) == gs_blur(tmp, src, r); gs_sobel(dst, tmp) bit for bit (dst's 1-px
+// frame untouched, like gs_sobel), with 1 B/px read + 1 B/px written instead of 4 B/px: the c2 pair of
+// BASELINE.json is HBM-bound, and its intermediate was half of its traffic.  Same walk as k_box_tma: a warp
+// rolls the box sums down its band and gets each blurred row as 8 packed bytes per lane; instead of storing
+// them, the lane fetches its neighbours' edge words by two shuffles and feeds the row to gs_sobel's 16-bit
+// lane-pair arithmetic (pairs.cuh), keeping the horizontal partials of the previous two blurred rows in
+// registers.  A band of 32 sobel rows needs 34 blurred rows, and sobel needs the blurred columns x-1 / x+8
+// of the neighbouring lanes, so lanes 2..29 produce outputs: tiles advance 224 columns.
+#ifndef GSB_BS_UNROLL
+#define GSB_BS_UNROLL 0                       // 0: the interior band loop is fully unrolled (34 rows)
+#endif
+constexpr int BS_UNROLL = GSB_BS_UNROLL > 0 ? GSB_BS_UNROLL : BX_BH + 2;
+constexpr int BS_STRIDE = 224;
+constexpr int BS_TILE_WORDS = BX_PW * (BX_TH + 2 + 2 * BX_RMAX);
+constexpr int BS_SMEM = BS_TILE_WORDS * 4 + 226 * 8 + 16;
+
+template <int R>
+__global__ void __launch_bounds__(BX_THREADS)
+k_blur_sobel_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, unsigned w, unsigned h) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t *tile = reinterpret_cast<uint32_t *>(smem_raw);
+  float2 *magic = reinterpret_cast<float2 *>(smem_raw + BS_TILE_WORDS * 4);
+  uint64_t &bar = *reinterpret_cast<uint64_t *>(smem_raw + BS_TILE_WORDS * 4 + 226 * 8);
+  constexpr int ROWS = BX_TH + 2 + 2 * R;
+  constexpr int FULL = 2 * R + 1;
+
+  const unsigned frame = blockIdx.z;
+  const int xb = (int)blockIdx.x * BS_STRIDE - 16;   // image column of tile byte 0 (16-B aligned)
+  const int y0 = (int)blockIdx.y * BX_TH;            // first sobel row of the tile
+  // every window of the blurred pixels this tile needs (rows y0-1 .. y0+TH, columns xb+8 .. xb+247) is unclipped
+  const bool interior = xb + 8 - R >= 0 && xb + 8 + BX_STRIDE - 1 + R <= (int)w - 1 && y0 - 1 - R >= 0 &&
+                        y0 + BX_TH + R <= (int)h - 1;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (!interior) {
+    for (unsigned c = threadIdx.x + 1; c < 226; c += BX_THREADS) {
+      const DivMagic d = div_magic(c);
+      magic[c] = make_float2(d.inv, d.k);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, BX_PW * 4 * ROWS);
+    tma_load_3d(tile, &tmap, xb / 4, y0 - 1 - R, frame, &bar);
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x = xb + 8 * lane;
+  const int yb = y0 + warp * BX_BH;            // first sobel row of this warp's band; blurred rows yb-1 .. yb+BH
+  const bool blur_lane = lane >= 1 && lane <= 30 && x >= 0 && x < (int)w;
+  const bool out_lane = lane >= 2 && lane <= 29 && x < (int)w;
+  const uint32_t *in = tile + (warp * BX_BH) * BX_PW + 2 * lane;   // tile row of image row yb - 1 - R
+  uint8_t *outp = dst + (size_t)frame * w * h + (size_t)yb * w + x;
+  int cw[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) cw[j] = blur_lane ? min(x + j + R, (int)w - 1) - max(x + j - R, 0) + 1 : 1;
+  const bool edge_l = x == 0, edge_r = x + 8 == (int)w;
+
+  mbar_wait(&bar, 0);
+  if (yb >= (int)h - 1) return;                // warp-uniform: no sobel row of this band is written
+
+  uint32_t S[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 2 * R; i++) {
+    uint32_t e[4];
+    unpack_pairs(*reinterpret_cast<const uint2 *>(in + i * BX_PW), e);
+#pragma unroll
+    for (int k = 0; k < 4; k++) S[k] += e[k];
+  }
+  uint32_t L[4] = {0, 0, 0, 0};
+
+  // blurred row j of the band (image row yb - 1 + j) as 8 packed bytes
+  auto blur_row = [&](int j, auto interior_tag) -> uint2 {
+    constexpr bool INT = decltype(interior_tag)::value;
+    uint32_t e[4];
+    unpack_pairs(*reinterpret_cast<const uint2 *>(in + (j + 2 * R) * BX_PW), e);
+#pragma unroll
+    for (int k = 0; k < 4; k++) S[k] = S[k] + e[k] - L[k];
+    unpack_pairs(*reinterpret_cast<const uint2 *>(in + j * BX_PW), L);
+    uint32_t V[12], T[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      V[4 + k] = S[k];
+      V[k] = (R == 7 || k > 0) ? __shfl_up_sync(0xFFFFFFFFu, S[k], 1) : 0u;
+      V[8 + k] = (R == 7 || k < 3) ? __shfl_down_sync(0xFFFFFFFFu, S[k], 1) : 0u;
+    }
+    window_sums<R>(V, T);
+    int ch = FULL;
+    if (!INT) {
+      const int y = yb - 1 + j;
+      ch = max(min(y + R, (int)h - 1) - max(y - R, 0) + 1, 1);   // rows outside the image are never used
+    }
+    return box_finish<R, false, INT>(T, make_uint2(0, 0), cw, ch, magic, 0);
+  };
+
+  SobelRow ra, rb;
+  auto sobel_step = [&](int j, uint2 o, bool write_row) {
+    const uint32_t wl = __shfl_up_sync(0xFFFFFFFFu, o.y, 1);      // blurred bytes x-4 .. x-1
+    const uint32_t wr = __shfl_down_sync(0xFFFFFFFFu, o.x, 1);    // blurred bytes x+8 .. x+11
+    const SobelRow rc = sobel_row(split_pairs(wl, o.x, o.y, wr));
+    if (j >= 2) {
+      if (write_row && out_lane) {
+        uint2 so = sobel_out(ra, rb, rc);
+        if (edge_l) so.x = (so.x & 0xFFFFFF00u) | outp[0];                      // keep dst(0, y)
+        if (edge_r) so.y = (so.y & 0x00FFFFFFu) | ((uint32_t)outp[7] << 24);    // keep dst(w-1, y)
+        st_cs_u2(outp, so);
+      }
+      outp += w;
+    }
+    ra = rb;
+    rb = rc;
+  };
+
+  if (interior) {
+#pragma unroll BS_UNROLL
+    for (int j = 0; j < BX_BH + 2; j++) sobel_step(j, blur_row(j, std::true_type{}), true);
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < BX_BH + 2; j++) {
+      const int ys = yb + j - 2;                 // the sobel row completed by blurred row j
+      if (ys > (int)h - 2) break;                // warp-uniform
+      sobel_step(j, blur_row(j, std::false_type{}), ys >= 1);
+    }
+  }
+}
+
 // ---- wide radii (8 <= r <= 120): radius-independent work, u32 window sums -------------------
 // The reference's own smoke runs use `blur 9` and `adaptive 15 5` (reference Makefile:17,20); the generic
 // kernel below costs (2r+1)^2 taps per pixel there.  This one costs the same ~14 instructions per pixel for
@@ -521,9 +652,48 @@ static int launch_box(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, 
   return 0;
 }
 
+template <int R>
+static int launch_blur_sobel_r(const CUtensorMap &tmap, uint8_t *dst, unsigned w, unsigned h, unsigned n, cudaStream_t s) {
+  const unsigned tiles_x = (w + BS_STRIDE - 1) / BS_STRIDE, tiles_y = (h + BX_TH - 1) / BX_TH;
+  GSB_ASSERT(tiles_y <= 65535u && n <= 65535u);
+  static DeviceOnce once;
+  if (once.needed()) {
+    GSB_CHECK(cudaFuncSetAttribute(k_blur_sobel_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM));
+    once.done();
+  }
+  k_blur_sobel_tma<R><<<dim3(tiles_x, tiles_y, n), BX_THREADS, BS_SMEM, s>>>(tmap, dst, w, h);
+  GSB_LAUNCHED(1);
+  return 0;
+}
+
 }  // namespace gsb
 
 extern "C" {
+int gs_b200_blur_sobel_batch(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, unsigned n, unsigned radius,
+                             gs_b200_stream st) {
+  GSB_ASSERT(dst && src && w > 0 && h > 0);  // reference :269, :307
+  cudaStream_t s = static_cast<cudaStream_t>(st);
+  if (n == 0 || w < 3 || h < 3) return 0;    // gs_sobel writes nothing below 3x3 (reference :308-309)
+  CUtensorMap tmap;
+  if (radius >= 1 && radius <= gsb::BX_RMAX && gsb::tma_ok(src, w) && gsb::tma_ok(dst, w) && n <= 65535u &&
+      gsb::make_tmap_u8frames(&tmap, src, w, h, n, gsb::BX_PW, gsb::BX_TH + 2 + 2 * radius)) {
+    switch (radius) {
+      case 1: return gsb::launch_blur_sobel_r<1>(tmap, dst, w, h, n, s);
+      case 2: return gsb::launch_blur_sobel_r<2>(tmap, dst, w, h, n, s);
+      case 3: return gsb::launch_blur_sobel_r<3>(tmap, dst, w, h, n, s);
+      case 4: return gsb::launch_blur_sobel_r<4>(tmap, dst, w, h, n, s);
+      case 5: return gsb::launch_blur_sobel_r<5>(tmap, dst, w, h, n, s);
+      case 6: return gsb::launch_blur_sobel_r<6>(tmap, dst, w, h, n, s);
+      default: return gsb::launch_blur_sobel_r<7>(tmap, dst, w, h, n, s);
+    }
+  }
+  // other radii / ragged widths: the two per-op kernels through a scratch frame batch (same result, 4 B/px)
+  uint8_t *tmp = static_cast<uint8_t *>(gsb::workspace(s, gsb::WS_STAGE_FUSED, (size_t)w * h * n));
+  if (!tmp) return (int)cudaErrorMemoryAllocation;
+  int rc = gs_b200_blur_batch(tmp, src, w, h, n, radius, st);
+  if (rc) return rc;
+  return gs_b200_sobel_batch(dst, tmp, w, h, n, st);
+}
 int gs_b200_blur_batch(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, unsigned n,
                        unsigned radius, gs_b200_stream s) {
   GSB_ASSERT(dst && src && w > 0 && h > 0);  // reference :269

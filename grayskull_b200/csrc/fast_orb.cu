@@ -380,6 +380,236 @@ k_fast_score_tiled(const __grid_constant__ CUtensorMap tmap, const uint8_t *__re
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_fast_tiled2: FAST score AND the 3x3 non-maximum mask of a tile in one kernel (round 2).
+// Round 1 ran k_nms_mask as a second, latency-bound pass over the score map (1.1 TB/s) that the score kernel
+// had just held in shared memory.  Here a CTA scores an 18-row x 130-column region -- its 16 x 128 tile plus a
+// 1-pixel ring, recomputed instead of exchanged -- and derives the tile's NMS bits straight from shared memory.
+// Ring cells that FAST never writes (x = 2, x = w-3, y = 2, y = h-3: whatever the caller left in the map takes
+// part in the NMS, reference :517-524) are fetched from the global score map; nobody writes those, so there is
+// no race between tiles.  Outputs: the score tile (interior pixels only), the per-row survivor bit masks
+// (pixel x -> bit x & 31 of word x >> 5) and per-row survivor counts (atomicAdd; zeroed by the launcher).
+// The compass pre-test is the tighter "two ADJACENT compass points": nine consecutive ring positions always
+// contain two consecutive multiples of four, so a corner needs (p0|p8) & (p4|p12) on the brighter or on the
+// darker side -- fewer candidates for the 16-sample test than round 1's "any two of four".
+// ---------------------------------------------------------------------------------------------
+constexpr int F2_TH = 64;                          // tile rows (4x round 1's: the per-thread set-up is paid once per 64 rows)
+constexpr int F2_ROWS = F2_TH + 2;                 // scored rows: y0-1 .. y0+64
+constexpr int F2_SH = F2_ROWS + 6;                 // source rows: y0-4 .. y0+67
+constexpr int F2_PITCH = 136;                      // score pitch: column lx (-1 .. 128) at byte lx + 4
+constexpr int F2_THREADS = 288;                    // 9 warps; warp q scores rows q, q+9, .. (8 of them)
+constexpr int F2_KROWS = 8;
+
+template <bool TMA>
+__global__ void __launch_bounds__(F2_THREADS)
+k_fast_tiled2(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ src, unsigned w, unsigned h,
+              uint8_t *__restrict__ score, unsigned t, unsigned mw, unsigned *__restrict__ masks,
+              unsigned *__restrict__ rowcount) {
+  __shared__ __align__(128) uint8_t s_src[F2_SH * FT_SW];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(16) uint8_t s_score[F2_ROWS * F2_PITCH];
+  __shared__ uint16_t s_list[F2_ROWS * 130];       // candidate = (row << 8) | (column + 4)
+  __shared__ unsigned s_cnt;
+  const unsigned f = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * FT_W, y0 = 3 + blockIdx.y * F2_TH;   // tile = columns [x0, x0+128), rows [y0, y0+64)
+  const int iw = (int)w, ih = (int)h, ti = (int)min(t, 255u);
+  const uint8_t *img = src + (size_t)f * w * h;
+  if (tid == 0) s_cnt = 0;
+  if (TMA) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, F2_SH * FT_SW);
+      tma_load_3d(s_src, &tmap, (x0 - FT_X) / 4, y0 - 4, (int)f, &bar);   // out-of-image reads as 0, never used
+    }
+  } else {
+    for (int i = tid; i < F2_SH * FT_SW; i += F2_THREADS) {
+      const int r = i / FT_SW, c = i % FT_SW;
+      const int yy = min(max(y0 - 4 + r, 0), ih - 1), xx = min(max(x0 - FT_X + c, 0), iw - 1);
+      s_src[i] = __ldg(img + (size_t)yy * w + xx);
+    }
+  }
+  {
+    uint4 *z = reinterpret_cast<uint4 *>(s_score);
+    for (int i = tid; i < F2_ROWS * F2_PITCH / 16; i += F2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  const int lx = 4 * lane;
+  unsigned colmask = 0;                                     // interior columns: 3 <= x < w - 3
+#pragma unroll
+  for (int j = 0; j < 4; j++) colmask |= (unsigned)(x0 + lx + j >= 3 && x0 + lx + j + 3 < iw) << j;
+  if (TMA) mbar_wait(&bar, 0);
+  __syncthreads();
+
+  // phase A: pre-test.  Row ly (0..65) <-> image row y0 - 1 + ly <-> s_src row ly + 3.
+  {
+    const uint32_t kb = (0x7FFFu - (uint32_t)ti) * 0x10001u, kw = (0x7FFFu + (uint32_t)ti) * 0x10001u;
+    unsigned flags = 0;                                     // bit 4k + j: row warp + 9k, pixel j is a candidate
+    const uint32_t *col0 = reinterpret_cast<const uint32_t *>(s_src) + (FT_X / 4) + lane;
+#pragma unroll
+    for (int k = 0; k < F2_KROWS; k++) {
+      const int ly = (int)warp + 9 * k, y = y0 - 1 + ly;
+      if (ly >= F2_ROWS || y < 3 || y + 3 >= ih || colmask == 0) continue;
+      const uint32_t *rowc = col0 + (ly + 3) * (FT_SW / 4);
+      const uint32_t wl = rowc[-1], wc = rowc[0], wr = rowc[1];
+      const uint32_t up = rowc[-3 * (FT_SW / 4)], dn = rowc[3 * (FT_SW / 4)];
+      const uint32_t v12 = __funnelshift_r(wl, wc, 8);      // bytes x-3 .. x
+      const uint32_t v4 = __funnelshift_r(wc, wr, 24);      // bytes x+3 .. x+6
+      uint32_t pe, po, ve[4], vo[4];
+      pairs_eo(wc, pe, po);
+      pairs_eo(up, ve[0], vo[0]);
+      pairs_eo(v4, ve[1], vo[1]);
+      pairs_eo(dn, ve[2], vo[2]);
+      pairs_eo(v12, ve[3], vo[3]);
+      unsigned cbits = 0;
+#pragma unroll
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const uint32_t P = hlf ? po : pe;
+        const uint32_t q = kb - P, r = P + kb, wrap = kw - P;
+        uint32_t b[4], d[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const uint32_t V = hlf ? vo[i] : ve[i];
+          b[i] = V + q;                                     // bit 15 / 31: v > p + t
+          d[i] = r - V;                                     // bit 15 / 31: v < p - t (when t <= p)
+        }
+        const uint32_t adj_b = (b[0] | b[2]) & (b[1] | b[3]);
+        const uint32_t adj_d = (d[0] | d[2]) & (d[1] | d[3]);
+        const uint32_t adj_nb = ~((b[0] & b[2]) | (b[1] & b[3]));     // wrap case (t > p): darker = not brighter
+        const uint32_t cand = (adj_b | (wrap & adj_nb) | (~wrap & adj_d)) & 0x80008000u;
+        cbits |= (cand >> (15 - hlf)) & (1u << hlf);        // bit 15 -> pixel hlf
+        cbits |= cand >> (29 - hlf);                        // bit 31 -> pixel 2 + hlf
+      }
+      flags |= (cbits & colmask) << (4 * k);
+    }
+    // the two ring columns x0 - 1 and x0 + 128 (66 rows each): scalar form of the same pre-test
+    bool hc = false;
+    int hent = 0;
+    if (tid < 2 * F2_ROWS) {
+      const int hly = (int)tid >> 1, hlx = (tid & 1) ? FT_W : -1;
+      const int x = x0 + hlx, y = y0 - 1 + hly;
+      hent = (hly << 8) | (hlx + 4);
+      if (x >= 3 && x + 3 < iw && y >= 3 && y + 3 < ih) {
+        const uint8_t *c = s_src + (hly + 3) * FT_SW + (hlx + FT_X);
+        const int p = c[0], hi = p + ti, lo = p - ti;
+        const int v0 = c[-3 * FT_SW], v4 = c[3], v8 = c[3 * FT_SW], v12 = c[-3];
+        const bool b0 = v0 > hi, b1 = v4 > hi, b2 = v8 > hi, b3 = v12 > hi;
+        const bool wrp = ti > p;
+        const bool d0 = wrp ? !b0 : v0 < lo, d1 = wrp ? !b1 : v4 < lo, d2 = wrp ? !b2 : v8 < lo, d3 = wrp ? !b3 : v12 < lo;
+        hc = ((b0 || b2) && (b1 || b3)) || ((d0 || d2) && (d1 || d3));
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, flags != 0 || hc)) {
+      const unsigned c = __popc(flags) + (hc ? 1u : 0u);
+      unsigned incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += u;
+      }
+      unsigned base = 0;
+      if (lane == 31) base = atomicAdd(&s_cnt, incl);
+      base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - c;
+      if (hc) s_list[base++] = (uint16_t)hent;
+      while (flags) {
+        const int bit = __ffs(flags) - 1;
+        flags &= flags - 1;
+        s_list[base++] = (uint16_t)((((int)warp + 9 * (bit >> 2)) << 8) | (lx + (bit & 3) + 4));
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase B: the full 16-sample test on the dense candidate list
+  {
+    const unsigned ncand = s_cnt;
+    for (unsigned k = tid; k < ncand; k += F2_THREADS) {
+      const int e = s_list[k], ly = e >> 8, cx = e & 0xFF;                     // cx = lx + 4
+      const uint8_t *c = s_src + (ly + 3) * FT_SW + (cx - 4 + FT_X);
+      const int p = c[0], hi = p + ti, lo = p - ti;
+      unsigned bright = 0, dark = 0;
+      int mind = 255;
+#define FAST_TAP3(i_, dx, dy)                                                       \
+  {                                                                                 \
+    const int v = c[(dy) * FT_SW + (dx)];                                           \
+    bright = __funnelshift_l((unsigned)(hi - v), bright, 1);   /* bit = (v > hi) */  \
+    dark = __funnelshift_l((unsigned)(v - lo), dark, 1);       /* bit = (v < lo) */  \
+    mind = min(mind, abs(v - p));                                                   \
+  }
+      FAST_RING(FAST_TAP3)
+#undef FAST_TAP3
+      bright &= 0xFFFFu;
+      dark = (ti > p) ? (~bright & 0xFFFFu) : (dark & 0xFFFFu);                // reference :498 wrap
+      if (run9(bright) || run9(dark)) s_score[ly * F2_PITCH + cx] = (uint8_t)mind;
+    }
+    // Ring cells FAST never writes (x = 2, x = w-3, y = 2, y = h-3) keep the caller's bytes and take part in
+    // the NMS: fetch the ones this region contains (border tiles only; other non-interior cells are never read)
+    const bool border_tile = x0 < 4 || x0 + FT_W + 3 >= iw || y0 < 4 || y0 + F2_TH + 3 >= ih;
+    if (border_tile) {
+      const uint8_t *sm = score + (size_t)f * w * h;
+      for (int i = tid; i < 2 * F2_ROWS + 2 * 130; i += F2_THREADS) {
+        int x, y;
+        if (i < 2 * F2_ROWS) x = (i & 1) ? iw - 3 : 2, y = y0 - 1 + (i >> 1);
+        else x = x0 - 1 + ((i - 2 * F2_ROWS) >> 1), y = (i & 1) ? ih - 3 : 2;
+        const int lxx = x - x0, lyy = y - (y0 - 1);
+        if (lxx >= -1 && lxx <= FT_W && lyy >= 0 && lyy < F2_ROWS && x >= 0 && x < iw && y >= 0 && y < ih)
+          s_score[lyy * F2_PITCH + lxx + 4] = __ldg(sm + (size_t)y * w + x);
+      }
+    }
+  }
+  __syncthreads();
+
+  // phase C + D: write the tile's scores (interior pixels, a word per 4) and its NMS bits.  Warp wq = 0..7 owns tile
+  // rows wq, wq + 8, ..; a lane owns 4 pixels; all-zero score words (almost all) skip the neighbour tests.
+  if (warp < 8) {                                             // every lane stays in: warp collectives below
+    const unsigned rows = h - 6;
+    const bool full = colmask == 0xF && TMA;
+    const unsigned word = (unsigned)(x0 + lx) >> 5;
+    const bool mask_lane = (lane & 7) == 0 && word < mw;
+    uint8_t *q = score + (size_t)f * w * h + (size_t)(y0 + (int)warp) * w + x0 + lx;
+    unsigned *mrow = masks + ((size_t)f * rows + (unsigned)(y0 - 3 + (int)warp)) * mw + word;
+    unsigned *rc = rowcount + (size_t)f * rows + (unsigned)(y0 - 3 + (int)warp);
+    const uint8_t *srow = s_score + ((int)warp + 1) * F2_PITCH + 4 + lx;
+    for (int k = 0; k < F2_TH / 8; k++) {
+      const int y = y0 + (int)warp + 8 * k;
+      if (y + 3 >= ih) break;                                 // warp-uniform
+      const uint32_t v = *reinterpret_cast<const uint32_t *>(srow);
+      if (full) {
+        *reinterpret_cast<uint32_t *>(q) = v;
+      } else if (colmask) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if ((colmask >> j) & 1u) q[j] = (uint8_t)(v >> (8 * j));
+      }
+      unsigned nib = 0;
+      if (v != 0 && colmask) {
+        const uint8_t *a = srow - F2_PITCH, *c = srow + F2_PITCH;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const unsigned sc = (v >> (8 * j)) & 0xFFu;
+          if (sc != 0 && ((colmask >> j) & 1u)) {
+            const bool keep = a[j - 1] <= sc && a[j] <= sc && a[j + 1] <= sc && srow[j - 1] <= sc && srow[j + 1] <= sc &&
+                              c[j - 1] <= sc && c[j] <= sc && c[j + 1] <= sc;
+            nib |= (unsigned)keep << j;
+          }
+        }
+      }
+      unsigned m = 0;
+      if (__any_sync(0xFFFFFFFFu, nib != 0)) {               // rare: a surviving corner in this 128-pixel row piece
+        m = nib << (4 * (lane & 7));
+        m |= __shfl_xor_sync(0xFFFFFFFFu, m, 1);
+        m |= __shfl_xor_sync(0xFFFFFFFFu, m, 2);
+        m |= __shfl_xor_sync(0xFFFFFFFFu, m, 4);
+        if (mask_lane && m) atomicAdd(rc, __popc(m));
+      }
+      if (mask_lane) *mrow = m;
+      q += (size_t)8 * w, mrow += (size_t)8 * mw, rc += 8, srow += 8 * F2_PITCH;
+    }
+  }
+}
+
 // NMS in one pass: per interior row a bit mask of survivors (pixel x -> bit x & 31 of word x >> 5)
 // and their count.  A thread owns 4 pixels (one aligned word of the score row); all-zero words --
 // the common case -- skip the neighbour rows entirely.
@@ -831,26 +1061,41 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
   GSB_ASSERT(n <= 65535u && rows <= 0x7FFFFFFFu);
   // thresholds above 255 (the reference computes p + t / p - t in unsigned arithmetic, :496-498, which wraps for
   // huge t) take the literal per-pixel kernel: the tiled kernel's 16-bit lane arithmetic assumes t <= 255
-  if (sw == w && sh == h && !force_generic() && threshold <= 255u) {
-    dim3 grid((w + FT_W - 1) / FT_W, (h - 6 + FT_H - 1) / FT_H, n);
+  if (sw == w && sh == h && !force_generic() && threshold <= 255u && getenv("GS_B200_FAST_UNFUSED") == nullptr) {
+    // score + NMS mask in one kernel (k_fast_tiled2); the per-row counts are accumulated with atomics
+    dim3 grid((w + FT_W - 1) / FT_W, (h - 6 + F2_TH - 1) / F2_TH, n);
     GSB_ASSERT(grid.y <= 65535u);
+    GSB_CHECK(cudaMemsetAsync(rowcount, 0, sizeof(unsigned) * (size_t)rows * n, s));
     CUtensorMap tmap;
-    if (tma_ok(src, w) && tma_ok(score, w) && make_tmap_u8frames(&tmap, src, w, h, n, FT_SW / 4, FT_SH))
-      k_fast_score_tiled<true><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
+    if (tma_ok(src, w) && tma_ok(score, w) && make_tmap_u8frames(&tmap, src, w, h, n, FT_SW / 4, F2_SH))
+      k_fast_tiled2<true><<<grid, F2_THREADS, 0, s>>>(tmap, src, w, h, score, threshold, mw, masks, rowcount);
     else {
       memset(&tmap, 0, sizeof(tmap));
-      k_fast_score_tiled<false><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
+      k_fast_tiled2<false><<<grid, F2_THREADS, 0, s>>>(tmap, src, w, h, score, threshold, mw, masks, rowcount);
     }
-  } else {   // foreign-sized score map (single-image gs_fast only): gs_set semantics per pixel
-    dim3 block(32, 8), grid((w - 6 + 31) / 32, (h - 6 + 7) / 8, n);
-    k_fast_score<<<grid, block, 0, s>>>(src, w, h, n, score, sw, sh, threshold);
+    GSB_LAUNCHED(1);
+  } else {
+    if (sw == w && sh == h && !force_generic() && threshold <= 255u) {
+      dim3 grid((w + FT_W - 1) / FT_W, (h - 6 + FT_H - 1) / FT_H, n);
+      GSB_ASSERT(grid.y <= 65535u);
+      CUtensorMap tmap;
+      if (tma_ok(src, w) && tma_ok(score, w) && make_tmap_u8frames(&tmap, src, w, h, n, FT_SW / 4, FT_SH))
+        k_fast_score_tiled<true><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
+      else {
+        memset(&tmap, 0, sizeof(tmap));
+        k_fast_score_tiled<false><<<grid, 256, 0, s>>>(tmap, src, w, h, score, threshold);
+      }
+    } else {   // foreign-sized score map (single-image gs_fast only): gs_set semantics per pixel
+      dim3 block(32, 8), grid((w - 6 + 31) / 32, (h - 6 + 7) / 8, n);
+      k_fast_score<<<grid, block, 0, s>>>(src, w, h, n, score, sw, sh, threshold);
+    }
+    GSB_LAUNCHED(1);
+    if (sw % 4 == 0 && reinterpret_cast<uintptr_t>(score) % 4 == 0 && sw >= w && sh >= h)   // word pre-test stays inside the map
+      k_nms_mask<true><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
+    else
+      k_nms_mask<false><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
+    GSB_LAUNCHED(1);
   }
-  GSB_LAUNCHED(1);
-  if (sw % 4 == 0 && reinterpret_cast<uintptr_t>(score) % 4 == 0 && sw >= w && sh >= h)   // word pre-test stays inside the map
-    k_nms_mask<true><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
-  else
-    k_nms_mask<false><<<dim3((rows + 7) / 8, n), 256, 0, s>>>(score, sw, sh, w, h, mw, masks, rowcount);
-  GSB_LAUNCHED(1);
   k_row_scan<<<n, 1024, 0, s>>>(rowcount, rows, counts, nkps);
   GSB_LAUNCHED(1);
   const unsigned long long rows_total = (unsigned long long)rows * n;

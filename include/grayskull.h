@@ -13,9 +13,8 @@
  *       -DGS_UPSTREAM_HEADER='"/path/to/upstream/grayskull.h"'
  *     The upstream header is included unchanged; its hot-path definitions are renamed
  *     gs_cpu_<op> (still callable, handy for A/B checks) and the gs_<op> names resolve to the
- *     extern "C" entry points below.  Everything outside the hot path (crop, threshold,
- *     blobs, contours, template matching, PGM I/O ...) stays the upstream CPU code, so
- *     test.c and examples/nanomagick/nanomagick.c build unmodified.
+ *     extern "C" entry points below.  Everything else (crop, contour tracing, PGM I/O ...) stays
+ *     the upstream CPU code, so test.c and examples/nanomagick/nanomagick.c build unmodified.
  *
  *  2. Stand-alone mode (no upstream tree available): this header provides the types, the
  *     inline helpers callers use directly (gs_valid/gs_get/gs_set/gs_for/gs_integral_sum,
@@ -50,6 +49,9 @@
 #define gs_filter gs_cpu_filter
 #define gs_match_template gs_cpu_match_template
 #define gs_find_best_match gs_cpu_find_best_match
+#define gs_blobs gs_cpu_blobs
+#define gs_blob_corners gs_cpu_blob_corners
+#define gs_perspective_correct gs_cpu_perspective_correct
 #include GS_UPSTREAM_HEADER
 #undef gs_blur
 #undef gs_sobel
@@ -72,6 +74,9 @@
 #undef gs_filter
 #undef gs_match_template
 #undef gs_find_best_match
+#undef gs_blobs
+#undef gs_blob_corners
+#undef gs_perspective_correct
 
 #else
 /* ---- stand-alone mode --------------------------------------------------------------- */
@@ -96,6 +101,13 @@ struct gs_rect {
 };
 struct gs_point {
   unsigned x, y;
+};
+typedef uint16_t gs_label;
+struct gs_blob {
+  gs_label label;
+  unsigned area;
+  struct gs_rect box;
+  struct gs_point centroid;
 };
 struct gs_keypoint {
   struct gs_point pt;
@@ -289,6 +301,19 @@ void gs_filter(struct gs_image dst, struct gs_image src, struct gs_image kernel,
 void gs_match_template(struct gs_image img, struct gs_image tmpl, struct gs_image result);
 /* first strict maximum in raster order -- grayskull.h:725-738 */
 struct gs_point gs_find_best_match(struct gs_image result);
+
+/* 4-connected components of the pixels >= 128 -- grayskull.h:333-405.  labels: w*h gs_label, 0 =
+ * background; a component's label is the reference's: the rank (from 1) of its raster-first pixel among the
+ * pixels that start a run with no foreground pixel above them.  blobs[0..return) hold the components in label
+ * order (label, area, box {x, y, w, h}, centroid = coordinate sums / area in unsigned arithmetic); entries past
+ * the returned count are unspecified (the reference leaves first-pass leftovers there).  Running out of labels
+ * (more than nblobs run starts) behaves as in the reference: later pixels are labelled only through a labelled
+ * left / upper neighbour.  nblobs <= 65534. */
+unsigned gs_blobs(struct gs_image img, gs_label *labels, struct gs_blob *blobs, unsigned nblobs);
+/* extreme points of one blob in x+y / x-y, first in raster order on ties -- grayskull.h:407-421 */
+void gs_blob_corners(struct gs_image img, gs_label *labels, struct gs_blob *b, struct gs_point c[4]);
+/* bilinear warp of the quad c[0..3] (tl, tr, br, bl) onto dst, fp32 order of the reference -- grayskull.h:423-444 */
+void gs_perspective_correct(struct gs_image dst, struct gs_image src, struct gs_point c[4]);
 
 #ifdef __cplusplus
 }

@@ -64,6 +64,11 @@ int gs_b200_adaptive_threshold_batch(uint8_t *dst, const uint8_t *src, unsigned 
 /* gs_sobel, reference grayskull.h:306-320 (dst border bytes are left untouched) */
 int gs_b200_sobel_batch(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, unsigned n,
                         gs_b200_stream s);
+/* gs_blur(tmp, src, radius) followed by gs_sobel(dst, tmp) as ONE pass (reference grayskull.h:268-283 then
+ * :306-320): bit-identical to the two calls, dst border bytes left untouched, the blurred intermediate never
+ * written to memory -- 2 B/pixel of HBM traffic instead of 4 (BASELINE.json configs[1] is exactly this pair). */
+int gs_b200_blur_sobel_batch(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, unsigned n,
+                             unsigned radius, gs_b200_stream s);
 /* gs_erode / gs_dilate, reference grayskull.h:285-304 */
 int gs_b200_erode_batch(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, unsigned n,
                         gs_b200_stream s);
@@ -112,6 +117,21 @@ int gs_b200_match_template_batch(uint8_t *result, const uint8_t *img, unsigned w
 /* gs_find_best_match, reference grayskull.h:725-738, per result map */
 int gs_b200_find_best_match_batch(struct gs_point *best, const uint8_t *result, unsigned rw, unsigned rh,
                                   unsigned n, gs_b200_stream s);
+
+/* ---- connected components / perspective warp ---------------------------------- */
+/* gs_blobs, reference grayskull.h:333-405, over n frames.  labels: n*w*h gs_label; blobs: n x nblobs records, frame
+ * f's first counts[f] entries valid (label order), the rest untouched; counts: n unsigned.  nblobs <= 65534. */
+int gs_b200_blobs_batch(const uint8_t *img, unsigned w, unsigned h, unsigned n, gs_label *labels,
+                        struct gs_blob *blobs, unsigned *counts, unsigned nblobs, gs_b200_stream s);
+/* gs_blob_corners, reference grayskull.h:407-421: `blob` and `corners` (4 points: tl, tr, br, bl) in DEVICE memory */
+int gs_b200_blob_corners(const uint8_t *img, unsigned w, unsigned h, const gs_label *labels,
+                         const struct gs_blob *blob, struct gs_point *corners, gs_b200_stream s);
+/* gs_perspective_correct, reference grayskull.h:423-444, n source frames -> n dst frames.  per_frame == 0: corners =
+ * 4 points in HOST memory used for every frame; per_frame != 0: n x 4 points in DEVICE memory (e.g. written by
+ * gs_b200_blob_corners) */
+int gs_b200_perspective_correct_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *src, unsigned sw,
+                                      unsigned sh, unsigned n, const struct gs_point *corners, int per_frame,
+                                      gs_b200_stream s);
 
 /* ---- FAST / ORB ------------------------------------------------------------------------- */
 /* gs_fast, reference grayskull.h:482-534.  scoremap: n maps of w*h bytes, only the interior

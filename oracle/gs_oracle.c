@@ -341,12 +341,23 @@ GSO_API float gso_atan2f(float y, float x) {
   }
 }
 
-/* gs_compute_orientation, grayskull.h:608-621: the float accumulators there only ever hold
- * integers below 2^24 (r = 15: sum|dy| = 4528, x255 < 2^24), so int32 moments are identical */
+/* gs_compute_orientation, grayskull.h:608-621: for r <= 15 the float accumulators there only ever hold
+ * integers below 2^24 (r = 15: sum|dy| = 4528, x255 < 2^24), so int32 moments are identical; beyond
+ * that the sums can round, and the fp32 accumulation is repeated in the reference's dy-outer / dx-inner order */
 GSO_API float gso_compute_orientation(const uint8_t *img, unsigned w, unsigned h, unsigned x,
                                       unsigned y, unsigned r) {
   int m01 = 0, m10 = 0, ri = (int)r;
   (void)h;
+  if (r > 15) {
+    volatile float f01 = 0.0f, f10 = 0.0f;
+    for (int dy = -ri; dy <= ri; dy++)
+      for (int dx = -ri; dx <= ri; dx++)
+        if (dx * dx + dy * dy <= (int)(r * r)) {
+          int v = img[(size_t)((int)y + dy) * w + (size_t)((int)x + dx)];
+          f01 = f01 + (float)(dy * v), f10 = f10 + (float)(dx * v);
+        }
+    return gso_atan2f(f01, f10);
+  }
   for (int dy = -ri; dy <= ri; dy++)
     for (int dx = -ri; dx <= ri; dx++)
       if (dx * dx + dy * dy <= ri * ri) {
@@ -694,4 +705,146 @@ GSO_API unsigned gso_find_best_match(const uint8_t *result, unsigned w, unsigned
   for (unsigned k = 0; k < w * h; k++)
     if (result[k] > best_score) best_score = result[k], best = k;
   return best;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md 8(f) N4 -- gs_blobs / gs_blob_corners / gs_perspective_correct, grayskull.h:325-444.
+ *
+ * gs_blobs.  The reference labels in one raster pass with a union-find over provisional labels and a
+ * second pass that rewrites every label to its root.  Restated without provisional labels:
+ *   - a pixel receives a NEW label exactly when it is foreground (>= 128) and neither its left nor
+ *     its upper neighbour carries a label; while labels last every foreground pixel is labelled, so
+ *     these "seeds" are the run starts with no foreground pixel above them, numbered in raster order;
+ *   - unions always keep the smaller root, so a component's final label is the smallest seed number
+ *     in it = the seed number of its raster-first pixel;
+ *   - once `nblobs` seeds have been handed out (:349 "out of labels") no new label appears and a pixel
+ *     is labelled only through a labelled left / upper neighbour (:345-347 read labels, not pixels):
+ *     from the (nblobs+1)-th seed position on, mask(x,y) = fg(x,y) && (mask(x-1,y) || mask(x,y-1));
+ *   - components, areas, boxes and coordinate sums are those of the 4-connected components of `mask`.
+ * Components are found here by flood fill from each seed in raster order (the GPU uses a pixel
+ * union-find); blobs[0..m) in label order, centroid = sums / area in unsigned arithmetic (:397-398).
+ * ---------------------------------------------------------------------------------------- */
+GSO_API unsigned gso_blobs(const uint8_t *img, unsigned w, unsigned h, gs_label *labels, struct gs_blob *blobs,
+                           unsigned nblobs) {
+  size_t npx = (size_t)w * h;
+  uint8_t *mask = (uint8_t *)malloc(npx);
+  uint32_t *stack = (uint32_t *)malloc(npx * sizeof(uint32_t));
+  unsigned nseeds = 0, m = 0;
+  int overflow = 0;
+  for (size_t i = 0; i < npx; i++) labels[i] = 0;
+  for (unsigned y = 0; y < h; y++)
+    for (unsigned x = 0; x < w; x++) {
+      size_t i = (size_t)y * w + x;
+      int fg = img[i] >= 128;
+      int left = x > 0 && mask[i - 1], top = y > 0 && mask[i - w];
+      if (!overflow) {
+        mask[i] = (uint8_t)fg;
+        if (fg && !left && !top) {
+          if (nseeds == nblobs) overflow = 1, mask[i] = 0;   /* the first seed that finds no label left */
+          else nseeds++;
+        }
+      } else {
+        mask[i] = (uint8_t)(fg && (left || top));
+      }
+    }
+  /* flood fill in raster order: the first unlabelled mask pixel met is its component's raster-first pixel = a seed */
+  unsigned seed_no = 0;
+  for (unsigned y = 0; y < h; y++)
+    for (unsigned x = 0; x < w; x++) {
+      size_t i = (size_t)y * w + x;
+      if (!mask[i]) continue;
+      int left = x > 0 && mask[i - 1], top = y > 0 && mask[i - w];
+      if (!left && !top) seed_no++;                 /* every seed consumes a number, component start or not */
+      if (labels[i]) continue;
+      /* a pixel reached here unlabelled is the raster-first pixel of a new component, hence a seed */
+      unsigned area = 0, minx = x, maxx = x, miny = y, maxy = y, sx = 0, sy = 0, top_of_stack = 0;
+      stack[top_of_stack++] = (uint32_t)i;
+      labels[i] = (gs_label)seed_no;
+      while (top_of_stack) {
+        uint32_t p = stack[--top_of_stack];
+        unsigned px = p % w, py = p / w;
+        area++, sx += px, sy += py;
+        if (px < minx) minx = px;
+        if (px > maxx) maxx = px;
+        if (py < miny) miny = py;
+        if (py > maxy) maxy = py;
+        if (px > 0 && mask[p - 1] && !labels[p - 1]) labels[p - 1] = (gs_label)seed_no, stack[top_of_stack++] = p - 1;
+        if (px + 1 < w && mask[p + 1] && !labels[p + 1]) labels[p + 1] = (gs_label)seed_no, stack[top_of_stack++] = p + 1;
+        if (py > 0 && mask[p - w] && !labels[p - w]) labels[p - w] = (gs_label)seed_no, stack[top_of_stack++] = p - w;
+        if (py + 1 < h && mask[p + w] && !labels[p + w]) labels[p + w] = (gs_label)seed_no, stack[top_of_stack++] = p + w;
+      }
+      memset(&blobs[m], 0, sizeof(blobs[m]));
+      blobs[m].label = (gs_label)seed_no, blobs[m].area = area;
+      blobs[m].box.x = minx, blobs[m].box.y = miny, blobs[m].box.w = maxx - minx + 1, blobs[m].box.h = maxy - miny + 1;
+      blobs[m].centroid.x = sx / area, blobs[m].centroid.y = sy / area;
+      m++;
+    }
+  free(mask);
+  free(stack);
+  return m;
+}
+
+/* gs_blob_corners, grayskull.h:407-421: over the blob's box, pixels >= 128 carrying its label; the four extremes of
+ * x+y (min -> tl, max -> br) and x-y (min -> bl, max -> tr), the FIRST pixel in raster order on ties (strict
+ * comparisons); all four default to the centroid.  Restated as key minima: (value, raster index). */
+GSO_API void gso_blob_corners(const uint8_t *img, unsigned w, unsigned h, const gs_label *labels, const struct gs_blob *b,
+                              struct gs_point c[4]) {
+  long long best[4] = {-1, -1, -1, -1};
+  int val[4] = {0, 0, 0, 0};
+  (void)h;
+  for (unsigned y = b->box.y; y < b->box.y + b->box.h; y++)
+    for (unsigned x = b->box.x; x < b->box.x + b->box.w; x++) {
+      if (x >= w || y >= h || img[(size_t)y * w + x] < 128 || labels[(size_t)y * w + x] != b->label) continue;
+      int sum = (int)x + (int)y, diff = (int)x - (int)y;
+      long long idx = (long long)y * w + x;
+      int cand[4] = {sum, -diff, -sum, diff};        /* tl: min sum, tr: max diff, br: max sum, bl: min diff */
+      for (int k = 0; k < 4; k++)
+        if (best[k] < 0 || cand[k] < val[k]) best[k] = idx, val[k] = cand[k];
+    }
+  for (int k = 0; k < 4; k++) {
+    if (best[k] < 0) c[k] = b->centroid;
+    else c[k].x = (unsigned)(best[k] % w), c[k].y = (unsigned)(best[k] / w);
+  }
+}
+
+/* gs_perspective_correct, grayskull.h:423-444.  fp32, the reference's evaluation order, no contraction: bilinear
+ * interpolation of the quad edges (c[0]=tl, c[1]=tr, c[2]=br, c[3]=bl) gives the source point, clamped to the image,
+ * then gs_resize-style bilinear sampling; dst.w == 1 / dst.h == 1 divide 0 by 0 like the reference (NaN clamps to the
+ * last column / row through the ternaries of GS_MIN / GS_MAX). */
+GSO_API void gso_perspective_correct(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *src, unsigned sw, unsigned sh,
+                                     const struct gs_point c[4]) {
+  volatile float w = (float)dw - 1.0f, h = (float)dh - 1.0f;
+  float c0x = (float)c[0].x, c0y = (float)c[0].y, c1x = (float)c[1].x, c1y = (float)c[1].y;
+  float c2x = (float)c[2].x, c2y = (float)c[2].y, c3x = (float)c[3].x, c3y = (float)c[3].y;
+  float mx = (float)sw - 1.0f, my = (float)sh - 1.0f;
+  for (unsigned y = 0; y < dh; y++)
+    for (unsigned x = 0; x < dw; x++) {
+      volatile float u = (float)x / w, v = (float)y / h;
+      volatile float omu = 1 - u, omv = 1 - v;
+      volatile float a, b2, top_x, top_y, bot_x, bot_y, src_x, src_y;
+      a = c0x * omu, b2 = c1x * u, top_x = a + b2;
+      a = c0y * omu, b2 = c1y * u, top_y = a + b2;
+      a = c3x * omu, b2 = c2x * u, bot_x = a + b2;
+      a = c3y * omu, b2 = c2y * u, bot_y = a + b2;
+      a = top_x * omv, b2 = bot_x * v, src_x = a + b2;
+      a = top_y * omv, b2 = bot_y * v, src_y = a + b2;
+      float fx = src_x < mx ? src_x : mx, fy = src_y < my ? src_y : my;   /* GS_MIN(src_x, w-1): NaN -> w-1 */
+      fx = 0.0f > fx ? 0.0f : fx;                                           /* GS_MAX(0, .) */
+      fy = 0.0f > fy ? 0.0f : fy;
+      unsigned x0 = (unsigned)fx, y0 = (unsigned)fy;
+      unsigned x1 = x0 + 1 < sw - 1 ? x0 + 1 : sw - 1, y1 = y0 + 1 < sh - 1 ? y0 + 1 : sh - 1;
+      volatile float dx = fx - (float)x0, dy = fy - (float)y0;
+      float c00 = src[(size_t)y0 * sw + x0], c01 = src[(size_t)y0 * sw + x1];
+      float c10 = src[(size_t)y1 * sw + x0], c11 = src[(size_t)y1 * sw + x1];
+      volatile float omx = 1 - dx, omy = 1 - dy;
+      volatile float t0 = c00 * omx, t1 = c01 * dx, t2 = c10 * omx, t3 = c11 * dx;
+      t0 = t0 * omy;
+      t1 = t1 * omy;
+      t2 = t2 * dy;
+      t3 = t3 * dy;
+      volatile float acc = t0 + t1;
+      acc = acc + t2;
+      acc = acc + t3;
+      dst[(size_t)y * dw + x] = (uint8_t)acc;
+    }
 }

@@ -102,6 +102,13 @@ def oracle():
         lib.gso_threshold.restype = None
         lib.gso_threshold.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
         lib.gso_match_orb.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_float]
+        lib.gso_blobs.restype = C.c_uint
+        lib.gso_blobs.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_uint]
+        lib.gso_blob_corners.restype = None
+        lib.gso_blob_corners.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gso_perspective_correct.restype = None
+        lib.gso_perspective_correct.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+        lib.gso_compute_orientation.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
         lib.gso_lbp_window.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_int,
                                        C.c_float]
         lib.gso_lbp_detect.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p,

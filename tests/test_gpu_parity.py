@@ -461,6 +461,13 @@ def test_reference_cli_overlay_vs_cpu(tmp_path):
     assert sorted(files_c) == sorted(files_o) and len(files_c) >= 20
     for name in files_c:
         assert files_c[name] == files_o[name], name
+    # the overlay build binds the whole hot path AND the 8(f) rows to the CUDA library: every one of these is an
+    # undefined (imported) symbol of the executable, none resolves to the upstream CPU body (gs_cpu_*)
+    nm = subprocess.run(["nm", "-D", "--undefined-only", exes["overlay"]], capture_output=True, text=True).stdout
+    for sym in ("gs_blur", "gs_sobel", "gs_adaptive_threshold", "gs_erode", "gs_dilate", "gs_resize", "gs_fast", "gs_orb_extract",
+                "gs_match_orb", "gs_integral", "gs_lbp_detect", "gs_threshold", "gs_otsu_threshold", "gs_blobs",
+                "gs_blob_corners", "gs_perspective_correct"):
+        assert (" U " + sym + "\n") in nm, sym
 
 
 def _o_hist(O, a):
@@ -822,3 +829,86 @@ def test_wide_radius_box_vs_oracle_and_reference_goldens(G, O):
     got = G.blur_batch(dev(f[None]), 15)[0].cpu().numpy()
     rng2 = np.random.default_rng(3)
     _crop_check(got, f, lambda a: o_blur(O, a, 15), 15, rng2)
+
+
+@pytest.mark.parametrize("force_generic", [0, 1])
+def test_fused_blur_sobel_vs_oracle_chain(G, O, force_generic):
+    """gs_b200_blur_sobel_batch == gs_blur -> gs_sobel bit for bit: every radius of the fused
+    kernel (1..7) and the two-kernel fall-back (0, 8, 15; ragged widths), dst pre-filled with 77 so that sobel's
+    untouched 1-px frame is checked, tile / band seams at 224-column and 32-row multiples"""
+    import grayskull_b200 as g
+    g.lib().gs_b200_force_generic(force_generic)
+    try:
+        rng = np.random.default_rng(23)
+        for (w, h) in [(256, 128), (272, 140), (512, 300), (16, 16), (48, 7), (1024, 67), (640, 480), (100, 37), (17, 1), (3, 3),
+                       (2, 9), (464, 259), (240, 34), (224, 33)]:
+            frames = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint8), L.natural_like(w, h, 5), np.full((h, w), 255, np.uint8)])
+            src = dev(frames)
+            for r in (0, 1, 2, 3, 4, 5, 6, 7, 8, 15):
+                got = G.blur_sobel_batch(src, r, out=dev(np.full_like(frames, 77))).cpu().numpy()
+                for i in range(3):
+                    want = o_sobel(O, o_blur(O, frames[i], r), 77)
+                    assert np.array_equal(got[i], want), (w, h, r, i)
+    finally:
+        g.lib().gs_b200_force_generic(0)
+    # full C2 frame size: equality with the two-call chain on the device
+    import torch
+    torch.manual_seed(4)
+    src = torch.randint(0, 256, (3, 4096, 4096), dtype=torch.uint8, device="cuda")
+    a = G.blur_sobel_batch(src, 5)
+    b = G.sobel_batch(G.blur_batch(src, 5))
+    assert bool((a == b).all())
+
+
+def test_blobs_corners_perspective_vs_reference_goldens_and_oracle(G, O):
+    """gs_blobs (labels = the reference's union-find numbering, running out of labels included),
+    gs_blob_corners, gs_perspective_correct -- against reference-generated goldens, the oracle on random binary
+    images, the batched ABI, and the reference's test.c vector"""
+    import torch
+    z = np.load(os.path.join(GOLD, "round2_golden.npz"))
+    for tag in z["blob_tags"]:
+        a = np.ascontiguousarray(z["blob_img_" + str(tag)])
+        for nb in (1000, 7, 1):
+            labels, blobs = G.gs_blobs(a, nb)
+            assert np.array_equal(labels, z["blob_%s_n%d_labels" % (tag, nb)]), (tag, nb)
+            assert np.array_equal(np.array(L.blob_fields(blobs), np.int64).reshape(-1, 8), z["blob_%s_n%d_blobs" % (tag, nb)]), (tag, nb)
+        key = "blob_%s_corners" % tag
+        if key in z.files:
+            labels, blobs = G.gs_blobs(a, 1000)
+            for j, want in enumerate(z[key]):
+                assert np.array_equal(G.gs_blob_corners(a, labels, blobs[j:j + 1]), want), (tag, j)
+    src = np.ascontiguousarray(z["persp_src"])
+    for qi, q in enumerate(z["persp_quads"]):
+        for (dw, dh) in ((160, 100), (33, 47), (1, 1), (2, 5)):
+            d = G.gs_perspective_correct(np.empty((dh, dw), np.uint8), src, q)
+            assert np.array_equal(d, z["persp_q%d_%dx%d" % (qi, dw, dh)]), (qi, dw, dh)
+    # test.c:232-257
+    Wv = 255
+    a = np.array([[Wv, Wv, 0, 0, Wv, 0], [Wv, 0, 0, Wv, Wv, 0], [0, 0, Wv, Wv, 0, 0], [Wv, Wv, Wv, 0, 0, Wv],
+                  [0, Wv, 0, 0, 0, Wv]], np.uint8)
+    _, blobs = G.gs_blobs(a, 10)
+    assert L.blob_fields(blobs) == [(1, 3, 0, 0, 2, 2, 0, 0), (2, 9, 0, 0, 5, 5, 2, 2), (6, 2, 5, 3, 1, 2, 5, 3)]
+    # batched ABI vs the oracle: ragged widths, wide frames (several mask-word chunks per row), label overflow
+    rng = np.random.default_rng(31)
+    for (w, h, nb) in ((100, 37, 500), (1300, 90, 4000), (640, 480, 3000), (64, 64, 5), (2200, 40, 60000), (33, 200, 2)):
+        frames = np.stack([L.binary_like(w, h, 50 + i, density=float(rng.uniform(0.3, 0.7)), smooth=int(rng.integers(0, 5))) for i in range(3)])
+        frames[2] = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        labels, blobs, counts = G.blobs_batch(dev(frames), nb)
+        lab = labels.cpu().numpy().view(np.uint16)
+        bl = blobs.cpu().numpy().view(np.uint32)
+        cnt = counts.cpu().numpy()
+        for i in range(3):
+            wl = np.zeros((h, w), np.uint16); wb = np.zeros(nb, L.BLOB_DTYPE)
+            m = O.gso_blobs(L.ptr(frames[i]), w, h, L.ptr(wl), L.ptr(wb), nb)
+            assert cnt[i] == m, (w, h, nb, i, cnt[i], m)
+            assert np.array_equal(lab[i], wl), (w, h, nb, i)
+            got = np.ascontiguousarray(bl[i, :m]).view(L.BLOB_DTYPE).reshape(-1)
+            assert L.blob_fields(got) == L.blob_fields(wb[:m]), (w, h, nb, i)
+    # perspective, batched with device-resident per-frame corners
+    frames = np.stack([L.natural_like(200, 150, 70 + i) for i in range(3)])
+    quads = rng.integers(0, 230, (3, 4, 2)).astype(np.int32)
+    out = G.perspective_correct_batch(dev(frames), 90, 70, torch.from_numpy(quads).cuda()).cpu().numpy()
+    for i in range(3):
+        want = np.empty((70, 90), np.uint8)
+        O.gso_perspective_correct(L.ptr(want), 90, 70, L.ptr(frames[i]), 200, 150, L.ptr(np.ascontiguousarray(quads[i].astype(np.uint32))))
+        assert np.array_equal(out[i], want), i

@@ -460,3 +460,108 @@ def test_golden_lena():
     cas = L.HostCascade()
     r = o_detect(cas, o_integral(a), 1000, 1.1, 1.0, 4.0, 2)
     assert r.tobytes() == z["lbp_rects"].tobytes() and len(r) == 10
+
+
+# ---- round 2: SURVEY.md 8(f) N4 rows and the r > 15 orientation -------------------------------------------
+def _o_blobs(a, nb):
+    labels = np.full(a.shape, 0x5555, np.uint16)
+    blobs = np.zeros(nb, L.BLOB_DTYPE)
+    m = O.gso_blobs(L.ptr(a), a.shape[1], a.shape[0], L.ptr(labels), L.ptr(blobs), nb)
+    return labels, blobs[:m]
+
+
+def _r_blobs(a, nb):
+    R = L.ref()
+    labels = np.full(a.shape, 0x5555, np.uint16)
+    blobs = np.zeros(nb, L.BLOB_DTYPE)
+    m = R.gs_blobs(L.img(a), L.ptr(labels), L.ptr(blobs), nb)
+    return labels, blobs[:m]
+
+
+def test_testc_blobs():  # reference test.c:232-257, same image and expectations
+    Wv = 255
+    a = np.array([[Wv, Wv, 0, 0, Wv, 0], [Wv, 0, 0, Wv, Wv, 0], [0, 0, Wv, Wv, 0, 0], [Wv, Wv, Wv, 0, 0, Wv],
+                  [0, Wv, 0, 0, 0, Wv]], np.uint8)
+    labels, blobs = _o_blobs(a, 10)
+    assert L.blob_fields(blobs) == [(1, 3, 0, 0, 2, 2, 0, 0), (2, 9, 0, 0, 5, 5, 2, 2), (6, 2, 5, 3, 1, 2, 5, 3)]
+
+
+@needs_ref
+def test_diff_blobs_corners():
+    rng = np.random.default_rng(77)
+    cases = 0
+    for i in range(60):
+        w, h = int(rng.integers(1, 90)), int(rng.integers(1, 70))
+        a = L.binary_like(w, h, 1000 + i, density=float(rng.uniform(0.2, 0.8)), smooth=int(rng.integers(0, 4)))
+        if i % 7 == 0:
+            a = rng.integers(0, 256, (h, w)).astype(np.uint8)             # grey noise: values around the 128 test
+        for nb in (2000, int(rng.integers(1, 30)), 1):
+            lo, bo = _o_blobs(a, nb)
+            lr, br = _r_blobs(a, nb)
+            assert np.array_equal(lo, lr), (i, w, h, nb)
+            assert L.blob_fields(bo) == L.blob_fields(br), (i, w, h, nb)
+            R = L.ref()
+            for j in range(min(len(br), 5)):
+                co, cr = np.zeros((4, 2), np.uint32), np.zeros((4, 2), np.uint32)
+                O.gso_blob_corners(L.ptr(a), w, h, L.ptr(lo), L.ptr(bo[j:j + 1]), L.ptr(co))
+                R.gs_blob_corners(L.img(a), L.ptr(lr), L.ptr(br[j:j + 1]), L.ptr(cr))
+                assert np.array_equal(co, cr), (i, nb, j)
+                cases += 1
+    assert cases > 200
+
+
+@needs_ref
+def test_diff_perspective_and_large_orientation():
+    R = L.ref()
+    rng = np.random.default_rng(78)
+    for i in range(40):
+        sw, sh = int(rng.integers(1, 120)), int(rng.integers(1, 90))
+        src = rng.integers(0, 256, (sh, sw)).astype(np.uint8)
+        dw, dh = int(rng.integers(1, 70)), int(rng.integers(1, 60))
+        c = rng.integers(0, max(sw, sh) + 30, (4, 2)).astype(np.uint32)
+        do, dr = np.empty((dh, dw), np.uint8), np.empty((dh, dw), np.uint8)
+        O.gso_perspective_correct(L.ptr(do), dw, dh, L.ptr(src), sw, sh, L.ptr(c))
+        R.gs_perspective_correct(L.img(dr), L.img(src), L.ptr(c))
+        assert np.array_equal(do, dr), (i, sw, sh, dw, dh)
+    a = np.clip(L.natural_like(300, 260, 5).astype(np.int32) + 100, 0, 255).astype(np.uint8)
+    for r in (2, 15, 16, 30, 64, 100):
+        for _ in range(6):
+            x, y = int(rng.integers(r, 300 - r)), int(rng.integers(r, 260 - r))
+            go = O.gso_compute_orientation(L.ptr(a), 300, 260, x, y, r)
+            gr = R.gs_compute_orientation(L.img(a), x, y, r)
+            assert np.float32(go).tobytes() == np.float32(gr).tobytes(), (x, y, r)
+
+
+def test_golden_round2_oracle_rows():
+    """the oracle against the reference-generated round-2 fixtures (runs without /root/reference)"""
+    z = np.load(os.path.join(L.ROOT, "tests", "golden", "round2_golden.npz"))
+    for tag in z["blob_tags"]:
+        a = np.ascontiguousarray(z["blob_img_" + str(tag)])
+        for nb in (1000, 7, 1):
+            lo, bo = _o_blobs(a, nb)
+            assert np.array_equal(lo, z["blob_%s_n%d_labels" % (tag, nb)]), (tag, nb)
+            assert np.array_equal(np.array(L.blob_fields(bo), np.int64).reshape(-1, 8), z["blob_%s_n%d_blobs" % (tag, nb)]), (tag, nb)
+        key = "blob_%s_corners" % tag
+        if key in z.files:
+            lo, bo = _o_blobs(a, 1000)
+            for j, want in enumerate(z[key]):
+                c = np.zeros((4, 2), np.uint32)
+                O.gso_blob_corners(L.ptr(a), a.shape[1], a.shape[0], L.ptr(lo), L.ptr(bo[j:j + 1]), L.ptr(c))
+                assert np.array_equal(c, want), (tag, j)
+    src = np.ascontiguousarray(z["persp_src"])
+    for qi, q in enumerate(z["persp_quads"]):
+        for (dw, dh) in ((160, 100), (33, 47), (1, 1), (2, 5)):
+            d = np.empty((dh, dw), np.uint8)
+            O.gso_perspective_correct(L.ptr(d), dw, dh, L.ptr(src), src.shape[1], src.shape[0], L.ptr(np.ascontiguousarray(q)))
+            assert np.array_equal(d, z["persp_q%d_%dx%d" % (qi, dw, dh)]), (qi, dw, dh)
+    a = np.ascontiguousarray(z["orient_img"])
+    for (x, y, r), want in zip(z["orient_xyr"], z["orient_angle"]):
+        got = O.gso_compute_orientation(L.ptr(a), a.shape[1], a.shape[0], int(x), int(y), int(r))
+        assert np.float32(got).tobytes() == np.float32(want).tobytes(), (x, y, r)
+    for tag in z["radius_tags"]:
+        a = np.ascontiguousarray(z["radius_img_" + str(tag)])
+        for r in z["radii"]:
+            d = np.empty_like(a); O.gso_blur(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], int(r))
+            assert np.array_equal(d, z["blur%d_%s" % (int(r), tag)])
+            d = np.empty_like(a); O.gso_adaptive_threshold(L.ptr(d), L.ptr(a), a.shape[1], a.shape[0], int(r), 5 - int(r))
+            assert np.array_equal(d, z["adaptive%d_%s" % (int(r), tag)])
