@@ -77,7 +77,7 @@ k_blob_seed(const unsigned *__restrict__ mask, unsigned h, unsigned mw, unsigned
     const unsigned k = k0 + lane;
     unsigned s = 0;
     if (k < mw) {
-      const unsigned cur = m[k], prev = k ? m[k - 1] : 0u, above = y ? m[k - mw] : 0u;
+      const unsigned cur = m[k], prev = k ? m[k - 1] : 0u, above = y ? (m - mw)[k] : 0u;   // (m - mw): k - mw would wrap
       s = cur & ~((cur << 1) | (prev >> 31)) & ~above;
       seed[gw * mw + k] = s;
     }

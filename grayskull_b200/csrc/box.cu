@@ -301,7 +301,9 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
 // registers.  A band of 32 sobel rows needs 34 blurred rows, and sobel needs the blurred columns x-1 / x+8
 // of the neighbouring lanes, so lanes 2..29 produce outputs: tiles advance 224 columns.
 #ifndef GSB_BS_UNROLL
-#define GSB_BS_UNROLL 0                       // 0: the interior band loop is fully unrolled (34 rows)
+#define GSB_BS_UNROLL 6                       // rows per unrolled step of the interior band loop (0: all 34; measured:
+                                              // 34 -> 1.01 ms, 6 -> 0.86 ms, 3 -> 0.87 ms per 64 frames; the full unroll
+                                              // is 74 KB of SASS and stalls on instruction fetch)
 #endif
 constexpr int BS_UNROLL = GSB_BS_UNROLL > 0 ? GSB_BS_UNROLL : BX_BH + 2;
 constexpr int BS_STRIDE = 224;
@@ -441,7 +443,9 @@ template <bool ADAPTIVE, bool ALIGNED>
 __global__ void __launch_bounds__(128)
 k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int h, int r, int R8, int BH,
            int strips, int cparam, float minv, int fast_ok) {
-  __shared__ __align__(16) uint32_t sp_all[4][2][264];
+  // prefix row of a warp, transposed: P(8 l + k) lives at [k][16 + l], so that for a fixed register index k the 32
+  // lanes touch 32 consecutive words (the natural [8 l + k] layout is an 8-way bank conflict on every read)
+  __shared__ uint32_t sp_all[4][2][8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = (int)blockIdx.x * 4 + warp;
   if (strip >= strips) return;                                  // warp-uniform; no CTA barriers below
@@ -480,7 +484,9 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
   }
   uint2 en = ld(yb + r + 1), lv = ld(yb - r), cen = make_uint2(0u, 0u);
   if (ADAPTIVE) cen = ld(yb);
-  uint32_t *sp0 = sp_all[warp][0], *sp1 = sp_all[warp][1];
+  uint32_t (*sp0)[64] = sp_all[warp][0], (*sp1)[64] = sp_all[warp][1];
+  if (lane == 0) sp0[7][15] = 0u, sp1[7][15] = 0u;              // P(-1) = 0
+  __syncwarp();
 
   for (int y = yb; y < ye; y++) {
     const uint2 en2 = ld(y + r + 2), lv2 = ld(y + 1 - r);
@@ -499,17 +505,17 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
       if (lane >= o) incl += t;
     }
     const uint32_t excl = incl - p[7];
-    uint32_t *sp = ((y - yb) & 1) ? sp1 : sp0;
-    uint4 *spw = reinterpret_cast<uint4 *>(sp + 4 + 8 * lane);   // P(i) lives at sp[i + 4]; sp[3] = P(-1)
-    spw[0] = make_uint4(p[0] + excl, p[1] + excl, p[2] + excl, p[3] + excl);
-    spw[1] = make_uint4(p[4] + excl, p[5] + excl, p[6] + excl, p[7] + excl);
-    if (lane == 0) sp[3] = 0u;                                    // P(-1) = 0
+    uint32_t (*sp)[64] = ((y - yb) & 1) ? sp1 : sp0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sp[k][16 + lane] = p[k] + excl;
     __syncwarp();
     if (out_lane) {
-      const int i0 = 8 * lane;
       uint32_t W[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) W[k] = sp[4 + i0 + k + r] - sp[3 + i0 + k - r];
+      for (int k = 0; k < 8; k++) {
+        const int ca = k + r, cb = k - r - 1 + 128;              // column offsets relative to 8 * lane (cb biased: >= 0)
+        W[k] = sp[ca & 7][16 + lane + (ca >> 3)] - sp[cb & 7][lane + (cb >> 3)];
+      }
       const int ch = min(y + r, h - 1) - max(y - r, 0) + 1;
       uint32_t q[8];
       if (fast_ok && cols_full && ch == FULL) {

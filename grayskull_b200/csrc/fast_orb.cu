@@ -1061,7 +1061,8 @@ static int fast_impl(const uint8_t *src, unsigned w, unsigned h, unsigned n, uin
   GSB_ASSERT(n <= 65535u && rows <= 0x7FFFFFFFu);
   // thresholds above 255 (the reference computes p + t / p - t in unsigned arithmetic, :496-498, which wraps for
   // huge t) take the literal per-pixel kernel: the tiled kernel's 16-bit lane arithmetic assumes t <= 255
-  if (sw == w && sh == h && !force_generic() && threshold <= 255u && getenv("GS_B200_FAST_UNFUSED") == nullptr) {
+  const char *unf = getenv("GS_B200_FAST_UNFUSED");     // A/B hook: 1 = round 1's two kernels (score, then NMS mask)
+  if (sw == w && sh == h && !force_generic() && threshold <= 255u && !(unf && unf[0] && unf[0] != '0')) {
     // score + NMS mask in one kernel (k_fast_tiled2); the per-row counts are accumulated with atomics
     dim3 grid((w + FT_W - 1) / FT_W, (h - 6 + F2_TH - 1) / F2_TH, n);
     GSB_ASSERT(grid.y <= 65535u);

@@ -188,6 +188,126 @@ k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, uns
 #undef IB_LOAD_ROW
 }
 
+// ---- round 2: k_integral_strips -- no inter-CTA chain on table rows ---------------------------------------------
+// k_integral_bands (below the batch threshold, kept) chains the bands of a frame through a 16 KB table row and a
+// flag: ncu showed 35 % of its stall samples on that spin and 0.69-0.71 of the HBM roofline.  Here a CTA owns a
+// 1024-column STRIP of one frame and walks down ALL its 16-row bands, so the row above a band never leaves the
+// registers (top[8] per thread).  What a strip needs from its left neighbours is one scalar per row: the sum of
+// their band-local column prefixes, SAT(xs-1, y) - SAT(xs-1, y0-1).  Every strip publishes its own row totals
+// of band b as soon as its band-local scan is done (64-bit words carrying a band tag, so no flag / fence pair), and
+// a strip adds up the totals of the strips to its left -- they run in lockstep, nobody waits for a predecessor's
+// OUTPUT, only for its local phase.  Tickets are handed out strip-major, so a strip's left neighbours always hold
+// earlier tickets (they are resident or done: no deadlock).  HBM traffic: 1 B read + 4 B written per pixel.
+#ifndef GSB_IS_BH
+#define GSB_IS_BH 8
+#endif
+constexpr int IS_BH = GSB_IS_BH;              // rows per band of the strip kernel
+constexpr int IS_TPB = 128;                 // threads per CTA = 1024 columns
+constexpr int IS_SW = IS_TPB * 8;
+#ifndef GSB_IS_MINB
+#define GSB_IS_MINB 5
+#endif
+constexpr int IS_MINB = GSB_IS_MINB;         // CTAs per SM the register allocation must allow
+
+__global__ void __launch_bounds__(IS_TPB, IS_MINB)
+k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, unsigned w, unsigned h, unsigned n,
+                  unsigned strips, unsigned nbands, unsigned *__restrict__ ticket_ctr,
+                  unsigned long long *__restrict__ slots /* [n][strips][nbands][16] : tag << 32 | row total */) {
+  __shared__ uint32_t wtot[IS_BH][IS_TPB / 32];
+  __shared__ uint32_t lsum[IS_BH];
+  __shared__ uint32_t s_off[IS_BH][IS_TPB];   // exclusive horizontal offset of each thread inside its warp, per row
+  __shared__ unsigned s_ticket;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
+  __syncthreads();
+  const unsigned frame = s_ticket / strips, strip = s_ticket % strips;
+  const unsigned x = strip * IS_SW + tid * 8;
+  const bool live = x < w;
+  const uint8_t *sp = src + (size_t)frame * w * h + x;
+  uint32_t *dp = ii + (size_t)frame * w * h + x;
+  unsigned long long *myslots = slots + ((size_t)frame * strips + strip) * nbands * IS_BH;
+  uint32_t top[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+  for (unsigned band = 0; band < nbands; band++) {
+    const unsigned y0 = band * IS_BH, rows = min((unsigned)IS_BH, h - y0);
+    uint2 px[IS_BH];
+#pragma unroll
+    for (int r = 0; r < IS_BH; r++)
+      px[r] = (live && (unsigned)r < rows) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)(y0 + r) * w)) : make_uint2(0u, 0u);
+    // band-local: vertical prefix V (registers), per-row thread totals -> warp scan
+    {
+      uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < IS_BH; r++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          acc[c] += (px[r].x >> (8 * c)) & 0xFF;
+          acc[4 + c] += (px[r].y >> (8 * c)) & 0xFF;
+        }
+        const uint32_t t = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];
+        uint32_t incl = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= (unsigned)o) incl += u;
+        }
+        if (lane == 31) wtot[r][warp] = incl;
+        s_off[r][tid] = incl - t;
+      }
+    }
+    __syncthreads();
+    // strip totals per row -> publish; sums of the strips to the left -> lsum
+    if (tid < IS_BH) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int q = 0; q < IS_TPB / 32; q++) tot += wtot[tid][q];
+      if (strip + 1 < strips)
+        *reinterpret_cast<volatile unsigned long long *>(myslots + (size_t)band * IS_BH + tid) =
+            ((unsigned long long)(band + 1) << 32) | tot;
+      lsum[tid] = 0;
+    }
+    __syncthreads();
+    if (strip > 0 && tid < IS_BH * strip && tid < IS_TPB) {
+      // thread (j, r): total of strip j < strip for row r of this band (strips <= 8: at most 112 threads)
+      const unsigned j = tid / IS_BH, r = tid % IS_BH;
+      volatile unsigned long long *sl = slots + (((size_t)frame * strips + j) * nbands + band) * IS_BH + r;
+      unsigned long long v = *sl;
+      while ((unsigned)(v >> 32) != band + 1) {
+        __nanosleep(20);
+        v = *sl;
+      }
+      atomicAdd(&lsum[r], (uint32_t)v);
+    }
+    __syncthreads();
+    // emit the band's rows: SAT = top + left strips + warps to the left + lanes to the left + own prefix
+    if (live) {
+      uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < IS_BH; r++) {
+        if ((unsigned)r < rows) {
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            v[c] += (px[r].x >> (8 * c)) & 0xFF;
+            v[4 + c] += (px[r].y >> (8 * c)) & 0xFF;
+          }
+          uint32_t run = s_off[r][tid] + lsum[r];
+#pragma unroll
+          for (int q = 0; q < IS_TPB / 32; q++) run += (q < (int)warp) ? wtot[r][q] : 0u;
+#pragma unroll
+          for (int c = 0; c < 8; c++) run += v[c], o[c] = run + top[c];
+          uint4 *q4 = reinterpret_cast<uint4 *>(dp + (size_t)(y0 + r) * w);
+          q4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          q4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; c++) top[c] = o[c];          // the band's last row
+    }
+    __syncthreads();                                      // wtot / lsum are reused by the next band
+  }
+}
+
 }  // namespace gsb
 
 extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned w, unsigned h, unsigned n,
@@ -196,6 +316,23 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
   if (n == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const bool aligned = reinterpret_cast<uintptr_t>(src) % 8 == 0 && reinterpret_cast<uintptr_t>(ii) % 16 == 0;
+  {
+    const unsigned strips = (w + gsb::IS_SW - 1) / gsb::IS_SW, nbands = (h + gsb::IS_BH - 1) / gsb::IS_BH;
+    const unsigned long long ctas = (unsigned long long)n * strips;
+    const char *env = getenv("GS_B200_INTEGRAL");      // test / A-B hook: "bands" or "strips"
+    const bool want = env ? env[0] == 's' : ctas >= 148;
+    if (want && !(env && env[0] == 'b') && w % 8 == 0 && strips <= 8 && aligned && !gsb::force_generic() && ctas < 0x7FFFFFFFull) {
+      const size_t slot_bytes = sizeof(unsigned long long) * (size_t)ctas * nbands * gsb::IS_BH;
+      unsigned char *ws = static_cast<unsigned char *>(gsb::workspace(st, gsb::WS_INTEGRAL, 256 + slot_bytes));
+      if (!ws) return (int)cudaErrorMemoryAllocation;
+      GSB_CHECK(cudaMemsetAsync(ws, 0, 256 + (strips > 1 ? slot_bytes : 0), st));
+      gsb::k_integral_strips<<<(unsigned)ctas, gsb::IS_TPB, 0, st>>>(ii, src, w, h, n, strips, nbands,
+                                                                    reinterpret_cast<unsigned *>(ws),
+                                                                    reinterpret_cast<unsigned long long *>(ws + 256));
+      GSB_LAUNCHED(1);
+      return 0;
+    }
+  }
   if (n >= 32 && w % 8 == 0 && w <= 8192 && aligned && !gsb::force_generic() &&
       (unsigned long long)n * ((h + gsb::IB_BH - 1) / gsb::IB_BH) < 0x7FFFFFFFull) {
     const unsigned nbands = (h + gsb::IB_BH - 1) / gsb::IB_BH;

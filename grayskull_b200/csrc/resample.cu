@@ -75,15 +75,35 @@ __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c
   p = __fadd_rn(p, __fmul_rn(__fmul_rn(c11, dx), dy));
   return p;
 }
-__device__ __forceinline__ float byte_f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xFFu); }
+// u8 -> f32 and f32 -> u8 without the conversion pipe (I2F / F2I run at 16 lanes/clk/SM and four conversions per
+// dst pixel capped round 1's kernel at ~4 pixels/clk/SM): 0x4B0000bb is the float 2^23 + bb, so one PRMT (ALU pipe)
+// and one exact FADD (FMA pipe) give float(bb); adding 2^23 to p in [0, 256) with round-toward-zero leaves
+// trunc(p) in the low byte.
+__device__ __forceinline__ float byte_f(uint32_t w, int k) {
+  return __fsub_rn(__uint_as_float(prmt(w, 0x4B000000u, 0x7540u | (unsigned)k)), 8388608.0f);
+}
+__device__ __forceinline__ float u8_f(unsigned b) { return __fsub_rn(__uint_as_float(b | 0x4B000000u), 8388608.0f); }
+__device__ __forceinline__ uint32_t f_trunc_bits(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)); }  // low byte = (uint8_t)p
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src, unsigned sw,
          unsigned sh, unsigned n, bool src_aligned8) {
+  // the y-axis coefficients (an IEEE division each) of the CTA's 64 rows: once per CTA, not once per thread and row
+  __shared__ unsigned s_y0[8 * RS_ROWS], s_y1[8 * RS_ROWS];
+  __shared__ float s_dy[8 * RS_ROWS];
+  if (threadIdx.x < 8 * RS_ROWS) {
+    const unsigned yy = blockIdx.y * 8 * RS_ROWS + threadIdx.x;
+    unsigned a = 0, b = 0;
+    float fr = 0.0f;
+    if (yy < dh) resize_axis(yy, sh, dh, a, b, fr);
+    s_y0[threadIdx.x] = a, s_y1[threadIdx.x] = b, s_dy[threadIdx.x] = fr;
+  }
+  __syncthreads();
   const unsigned x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
   const unsigned yb = (blockIdx.y * 8 + (threadIdx.x >> 5)) * RS_ROWS;
   if (x >= dw || yb >= dh) return;
+  const unsigned yl = (threadIdx.x >> 5) * RS_ROWS;       // this warp's first row in the table
   unsigned x0[4], x1[4];
   float dx[4], omx[4];
 #pragma unroll
@@ -128,9 +148,8 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
 #endif
     for (unsigned r = 0; r < (unsigned)RS_ROWS && yb + r < dh; r++) {
       const unsigned y = yb + r;
-      unsigned y0, y1;
-      float dy;
-      resize_axis(y, sh, dh, y0, y1, dy);
+      const unsigned y0 = s_y0[yl + r], y1 = s_y1[yl + r];
+      const float dy = s_dy[yl + r];
       const float omy = __fsub_rn(1.0f, dy);
       const uint8_t *r0 = s + (size_t)y0 * sw, *r1 = s + (size_t)y1 * sw;
       uint32_t out = 0;
@@ -140,14 +159,13 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
         const float p1 = bilerp(byte_f(a.x, 2), byte_f(a.x, 3), byte_f(b.x, 2), byte_f(b.x, 3), omx[1], dx[1], omy, dy);
         const float p2 = bilerp(byte_f(a.y, 0), byte_f(a.y, 1), byte_f(b.y, 0), byte_f(b.y, 1), omx[2], dx[2], omy, dy);
         const float p3 = bilerp(byte_f(a.y, 2), byte_f(a.y, 3), byte_f(b.y, 2), byte_f(b.y, 3), omx[3], dx[3], omy, dy);
-        out = (__float2uint_rz(p0) & 0xFFu) | ((__float2uint_rz(p1) & 0xFFu) << 8) | ((__float2uint_rz(p2) & 0xFFu) << 16) |
-              ((__float2uint_rz(p3) & 0xFFu) << 24);
+        out = prmt(prmt(f_trunc_bits(p0), f_trunc_bits(p1), 0x0040), prmt(f_trunc_bits(p2), f_trunc_bits(p3), 0x0040), 0x5410);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const float c00 = (float)__ldg(r0 + x0[j]), c01 = (float)__ldg(r0 + x1[j]);
-          const float c10 = (float)__ldg(r1 + x0[j]), c11 = (float)__ldg(r1 + x1[j]);
-          out |= (__float2uint_rz(bilerp(c00, c01, c10, c11, omx[j], dx[j], omy, dy)) & 0xFFu) << (8 * j);
+          const float c00 = u8_f(__ldg(r0 + x0[j])), c01 = u8_f(__ldg(r0 + x1[j]));
+          const float c10 = u8_f(__ldg(r1 + x0[j])), c11 = u8_f(__ldg(r1 + x1[j]));
+          out |= (f_trunc_bits(bilerp(c00, c01, c10, c11, omx[j], dx[j], omy, dy)) & 0xFFu) << (8 * j);
         }
       }
       uint8_t *q = d + (size_t)y * dw + x;
@@ -185,6 +203,13 @@ int gs_b200_resize_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *
                          unsigned sh, unsigned n, gs_b200_stream s) {
   GSB_ASSERT(dst && src && dw > 0 && dh > 0 && sw > 0 && sh > 0);  // reference :172
   if (n == 0) return 0;
+  // Exact 2:1 in both axes: sx = ((x + 0.5) * 2dw) / dw - 0.5 = 2x + 0.5 with every fp32 step exact while
+  // (2x + 1) * dw < 2^24, so all four weights are 0.25, the products and their sum are exact, and the truncated
+  // result is (a + b + c + d) / 4 -- gs_downsample's arithmetic (reference :189-197), bit for bit.  Checked against
+  // the oracle's literal fp32 evaluation in tests/test_gpu_parity.py::test_stencils_vs_oracle (w/2, h/2 targets).
+  if (sw == 2 * dw && sh == 2 * dh && (unsigned long long)(2 * dw) * dw < (1ull << 24) &&
+      (unsigned long long)(2 * dh) * dh < (1ull << 24) && !gsb::force_generic())
+    return gs_b200_downsample_batch(dst, src, sw, sh, n, s);
   dim3 grid((dw + 127) / 128, (dh + 8 * gsb::RS_ROWS - 1) / (8 * gsb::RS_ROWS), n < 65535u ? n : 65535u);
   GSB_ASSERT(grid.y <= 65535u);
   const bool aligned8 = sw % 8 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0;   // every source row 8-byte aligned

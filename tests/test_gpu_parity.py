@@ -197,15 +197,24 @@ def test_stencils_vs_oracle(G, O, force_generic):
         g.lib().gs_b200_force_generic(0)
 
 
-def test_integral_single_pass_batches(G, O):
-    """batches of >= 32 frames take the single-pass chained-band kernel (integral.cu): ragged
-    heights, 1..32 warps per row, band counts from 1 to 135"""
-    for (w, h, n) in ((3840, 2160, 34), (256, 37, 33), (4096, 100, 32), (8192, 33, 32), (1920, 1080, 40), (8, 16, 32), (40, 17, 50)):
-        rng = np.random.default_rng(w + h)
-        fr = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
-        got = G.integral_batch(dev(fr)).cpu().numpy().view(np.uint32)
-        for i in (0, n // 2, n - 1):
-            assert np.array_equal(got[i], o_integral(O, fr[i])), (w, h, n, i)
+@pytest.mark.parametrize("kernel", ["bands", "strips", "auto"])
+def test_integral_single_pass_batches(G, O, kernel):
+    """the two single-pass kernels of integral.cu -- chained 16-row bands (round 1) and 1024-column strips walking
+    down the frame (round 2; the default once n * strips >= 148) -- on ragged heights, 1..8 strips per row (strip
+    seams at multiples of 1024 columns), band counts from 1 to 270, all-255 frames (the largest sums)"""
+    if kernel != "auto":
+        os.environ["GS_B200_INTEGRAL"] = kernel
+    try:
+        for (w, h, n) in ((3840, 2160, 40), (256, 37, 33), (4096, 100, 40), (8192, 33, 32), (1920, 1080, 80), (8, 16, 160), (40, 17, 150),
+                          (1032, 9, 75), (2048, 8, 74), (5000 // 8 * 8, 23, 40)):
+            rng = np.random.default_rng(w + h)
+            fr = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+            fr[n - 1] = 255
+            got = G.integral_batch(dev(fr)).cpu().numpy().view(np.uint32)
+            for i in (0, n // 2, n - 1):
+                assert np.array_equal(got[i], o_integral(O, fr[i])), (kernel, w, h, n, i)
+    finally:
+        os.environ.pop("GS_B200_INTEGRAL", None)
 
 
 def test_blur_constant_and_saturated(G, O):
