@@ -461,9 +461,10 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
   // all 8 pixels of this lane have the full (2r+1)-column window inside the image
   const bool cols_full = x0 - r >= 0 && x0 + 7 + r <= w - 1;
 
-  auto ld = [&](int y) -> uint2 {
+  // row loads by pointer (advanced by w per row; the per-row 64-bit multiply of y * w showed up as 10 % of the
+  // instructions in the first ncu capture)
+  auto ldp = [&](const uint8_t *p, int y) -> uint2 {
     if (!lane_in || y < 0 || y >= h) return make_uint2(0u, 0u);
-    const uint8_t *p = frame + (size_t)y * w + x0;
     if (ALIGNED) return __ldg(reinterpret_cast<const uint2 *>(p));
     uint32_t a = 0, b = 0;
 #pragma unroll
@@ -473,6 +474,7 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
     }
     return make_uint2(a, b);
   };
+  auto ld = [&](int y) -> uint2 { return ldp(frame + (ptrdiff_t)y * w + x0, y); };
 
   uint32_t S[4] = {0, 0, 0, 0};
 #pragma unroll 4
@@ -484,14 +486,26 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
   }
   uint2 en = ld(yb + r + 1), lv = ld(yb - r), cen = make_uint2(0u, 0u);
   if (ADAPTIVE) cen = ld(yb);
+  const uint8_t *p_en = frame + (ptrdiff_t)(yb + r + 2) * w + x0, *p_lv = frame + (ptrdiff_t)(yb + 1 - r) * w + x0;
+  const uint8_t *p_cen = frame + (ptrdiff_t)(yb + 1) * w + x0;
+  uint8_t *qo = out + (size_t)yb * w + x0;
+  // word offsets of P(i + r) and P(i - r - 1) in the transposed prefix row, for this lane's 8 pixels (row invariant)
+  int offA[8], offB[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int ca = k + r, cb = k - r - 1 + 128;                // cb biased by 16 lanes: >= 0
+    offA[k] = (ca & 7) * 64 + 16 + lane + (ca >> 3);
+    offB[k] = (cb & 7) * 64 + lane + (cb >> 3);
+  }
   uint32_t (*sp0)[64] = sp_all[warp][0], (*sp1)[64] = sp_all[warp][1];
   if (lane == 0) sp0[7][15] = 0u, sp1[7][15] = 0u;              // P(-1) = 0
   __syncwarp();
 
   for (int y = yb; y < ye; y++) {
-    const uint2 en2 = ld(y + r + 2), lv2 = ld(y + 1 - r);
+    const uint2 en2 = ldp(p_en, y + r + 2), lv2 = ldp(p_lv, y + 1 - r);
     uint2 cen2 = make_uint2(0u, 0u);
-    if (ADAPTIVE) cen2 = ld(y + 1);
+    if (ADAPTIVE) cen2 = ldp(p_cen, y + 1);
+    p_en += w, p_lv += w, p_cen += w;
     // ---- horizontal prefix of the column sums (u32)
     uint32_t p[8];
 #pragma unroll
@@ -511,11 +525,9 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
     __syncwarp();
     if (out_lane) {
       uint32_t W[8];
+      const uint32_t *spf = &sp[0][0];
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int ca = k + r, cb = k - r - 1 + 128;              // column offsets relative to 8 * lane (cb biased: >= 0)
-        W[k] = sp[ca & 7][16 + lane + (ca >> 3)] - sp[cb & 7][lane + (cb >> 3)];
-      }
+      for (int k = 0; k < 8; k++) W[k] = spf[offA[k]] - spf[offB[k]];
       const int ch = min(y + r, h - 1) - max(y - r, 0) + 1;
       uint32_t q[8];
       if (fast_ok && cols_full && ch == FULL) {
@@ -539,7 +551,6 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
       uint2 o;
       o.x = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
       o.y = q[4] | (q[5] << 8) | (q[6] << 16) | (q[7] << 24);
-      uint8_t *qo = out + (size_t)y * w + x0;
       if (ALIGNED) {
         st_cs_u2(qo, o);
       } else {
@@ -548,6 +559,7 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
           if (x0 + k >= 0 && x0 + k < w) qo[k] = (uint8_t)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
       }
     }
+    qo += w;
     // ---- roll the column sums down one row
     uint32_t e[4], l[4];
     unpack_pairs(en, e);

@@ -202,14 +202,13 @@ k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, uns
 #define GSB_IS_BH 8
 #endif
 constexpr int IS_BH = GSB_IS_BH;              // rows per band of the strip kernel
-constexpr int IS_TPB = 128;                 // threads per CTA = 1024 columns
-constexpr int IS_SW = IS_TPB * 8;
 #ifndef GSB_IS_MINB
-#define GSB_IS_MINB 5
+#define GSB_IS_MINB 4
 #endif
 constexpr int IS_MINB = GSB_IS_MINB;         // CTAs per SM the register allocation must allow
 
-__global__ void __launch_bounds__(IS_TPB, IS_MINB)
+template <int IS_TPB>
+__global__ void __launch_bounds__(IS_TPB, IS_MINB * 128 / IS_TPB)
 k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, unsigned w, unsigned h, unsigned n,
                   unsigned strips, unsigned nbands, unsigned *__restrict__ ticket_ctr,
                   unsigned long long *__restrict__ slots /* [n][strips][nbands][16] : tag << 32 | row total */) {
@@ -221,6 +220,7 @@ k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, un
   if (tid == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
   __syncthreads();
   const unsigned frame = s_ticket / strips, strip = s_ticket % strips;
+  constexpr int IS_SW = IS_TPB * 8;
   const unsigned x = strip * IS_SW + tid * 8;
   const bool live = x < w;
   const uint8_t *sp = src + (size_t)frame * w * h + x;
@@ -228,12 +228,22 @@ k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, un
   unsigned long long *myslots = slots + ((size_t)frame * strips + strip) * nbands * IS_BH;
   uint32_t top[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
+  // software pipeline: the pixel rows of band b + 1 are requested before band b is scanned and emitted, so that a
+  // CTA always has a band of loads in flight (without it the strips kernel ran at 0.48-0.71 of the HBM roofline)
+  uint2 pxn[IS_BH];
+#pragma unroll
+  for (int r = 0; r < IS_BH; r++)
+    pxn[r] = (live && (unsigned)r < h) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)r * w)) : make_uint2(0u, 0u);
   for (unsigned band = 0; band < nbands; band++) {
     const unsigned y0 = band * IS_BH, rows = min((unsigned)IS_BH, h - y0);
     uint2 px[IS_BH];
 #pragma unroll
-    for (int r = 0; r < IS_BH; r++)
-      px[r] = (live && (unsigned)r < rows) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)(y0 + r) * w)) : make_uint2(0u, 0u);
+    for (int r = 0; r < IS_BH; r++) px[r] = pxn[r];
+#pragma unroll
+    for (int r = 0; r < IS_BH; r++) {
+      const unsigned yn = y0 + IS_BH + r;
+      pxn[r] = (live && yn < h) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)yn * w)) : make_uint2(0u, 0u);
+    }
     // band-local: vertical prefix V (registers), per-row thread totals -> warp scan
     {
       uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -317,18 +327,27 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const bool aligned = reinterpret_cast<uintptr_t>(src) % 8 == 0 && reinterpret_cast<uintptr_t>(ii) % 16 == 0;
   {
-    const unsigned strips = (w + gsb::IS_SW - 1) / gsb::IS_SW, nbands = (h + gsb::IS_BH - 1) / gsb::IS_BH;
+    // 1024-column strips (128 threads) when that already fills the machine, else 512-column strips (64 threads)
+    const bool narrow = (unsigned long long)n * ((w + 1023) / 1024) < 592ull && w <= 4096;
+    const unsigned sw_cols = narrow ? 512u : 1024u;
+    const unsigned strips = (w + sw_cols - 1) / sw_cols, nbands = (h + gsb::IS_BH - 1) / gsb::IS_BH;
     const unsigned long long ctas = (unsigned long long)n * strips;
     const char *env = getenv("GS_B200_INTEGRAL");      // test / A-B hook: "bands" or "strips"
-    const bool want = env ? env[0] == 's' : ctas >= 148;
+    // measured (profiles/r02_ab_integral.txt): 256 UHD frames (1024 CTAs) strips 0.714 vs bands 0.713 of the HBM roofline;
+    // 64 frames of 4096^2 (512 narrow CTAs = 7 warps per SM) strips 0.66 vs bands 0.69 -- a strip is w/8 threads per
+    // frame however it is cut, so strips are the default only when the batch alone fills the machine
+    const bool want = env ? env[0] == 's' : (!narrow && ctas >= 592);
     if (want && !(env && env[0] == 'b') && w % 8 == 0 && strips <= 8 && aligned && !gsb::force_generic() && ctas < 0x7FFFFFFFull) {
       const size_t slot_bytes = sizeof(unsigned long long) * (size_t)ctas * nbands * gsb::IS_BH;
       unsigned char *ws = static_cast<unsigned char *>(gsb::workspace(st, gsb::WS_INTEGRAL, 256 + slot_bytes));
       if (!ws) return (int)cudaErrorMemoryAllocation;
       GSB_CHECK(cudaMemsetAsync(ws, 0, 256 + (strips > 1 ? slot_bytes : 0), st));
-      gsb::k_integral_strips<<<(unsigned)ctas, gsb::IS_TPB, 0, st>>>(ii, src, w, h, n, strips, nbands,
-                                                                    reinterpret_cast<unsigned *>(ws),
-                                                                    reinterpret_cast<unsigned long long *>(ws + 256));
+      if (narrow)
+        gsb::k_integral_strips<64><<<(unsigned)ctas, 64, 0, st>>>(ii, src, w, h, n, strips, nbands, reinterpret_cast<unsigned *>(ws),
+                                                                 reinterpret_cast<unsigned long long *>(ws + 256));
+      else
+        gsb::k_integral_strips<128><<<(unsigned)ctas, 128, 0, st>>>(ii, src, w, h, n, strips, nbands, reinterpret_cast<unsigned *>(ws),
+                                                                   reinterpret_cast<unsigned long long *>(ws + 256));
       GSB_LAUNCHED(1);
       return 0;
     }

@@ -76,6 +76,7 @@ struct TilePlan {              // host side, per scale: window tile of k_lbp_sca
   int twx, twy;                // windows per tile (twx a multiple of 32)
   int bw, ph;                  // box staged by TMA from EACH column-parity plane: bw x ph u32
   int tiles_x, tiles_y;
+  int threads;                 // LBP3_THREADS or LBP3_BIG_THREADS
   size_t smem;
 };
 struct DevCascade {            // pointers into one device blob
@@ -381,11 +382,17 @@ k_deinterleave2(uint32_t *__restrict__ planes, const uint32_t *__restrict__ ii, 
 #ifndef GSB_LBP3_THREADS
 #define GSB_LBP3_THREADS 512
 #endif
+#ifndef GSB_LBP_ROWDIFF
+#define GSB_LBP_ROWDIFF 1                     // measured: 63.26 -> 62.35 ms per 32 UHD frames
+#endif
 #ifndef GSB_LBP3_FLAT
 #define GSB_LBP3_FLAT 8        // a warp with this many survivors or fewer switches to the (window, weak) flat mode
 #endif
-constexpr int LBP3_THREADS = GSB_LBP3_THREADS;
+constexpr int LBP3_THREADS = GSB_LBP3_THREADS;   // small-window scales: two CTAs per SM
+constexpr int LBP3_BIG_THREADS = 1024;           // large-window scales: one CTA per SM with a tile up to 224 KB
+constexpr int LBP3_HIT_WORDS = 128;              // mask words of a tile: at most 4096 windows
 
+template <int LBP3_THREADS>
 __global__ void __launch_bounds__(LBP3_THREADS)
 k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int twx, int twy, int bw, int ph,
             int tiles_x, int flat_n, unsigned *__restrict__ masks) {
@@ -398,8 +405,8 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
   // 128-byte aligned start of it): tile | barrier, counters, 64 hit words | tables | survivor lists
   unsigned char *ctl = lsm + ((tile_bytes + 127u) & ~127u);
   uint64_t &bar = *reinterpret_cast<uint64_t *>(ctl);
-  unsigned *hit = reinterpret_cast<unsigned *>(ctl + 16);   // twy * (twx / 32) <= 64 mask words
-  TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 384);
+  unsigned *hit = reinterpret_cast<unsigned *>(ctl + 16);   // twy * (twx / 32) <= LBP3_HIT_WORDS mask words
+  TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 640);
   Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
   Stage *s_stage = reinterpret_cast<Stage *>(s_weak + dc.nweaks);
   int *s_sub = reinterpret_cast<int *>(s_stage + dc.nstages);
@@ -430,7 +437,7 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     for (int i = tid; i < dc.nstages * 2; i += LBP3_THREADS) d2[i] = g2[i];
     for (int i = tid; i < dc.nsubsets; i += LBP3_THREADS) s_sub[i] = dc.subsets[i];
   }
-  if (tid < 64) hit[tid] = 0;
+  if (tid < LBP3_HIT_WORDS) hit[tid] = 0;
   __syncthreads();
   mbar_wait(&bar, 0);
 
@@ -450,10 +457,23 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
       for (int k = 0; k < 4; k++) v[j][k] = *reinterpret_cast<const uint32_t *>(rb + g.col[k]);
     }
     uint32_t c[3][3];
+#if GSB_LBP_ROWDIFF
+    // cell = D + A - B - C as a difference of horizontal differences: 12 + 9 subtractions instead of 27 add/subs
+    uint32_t hd[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) hd[j][k] = v[j][k + 1] - v[j][k];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[j][k] = hd[j + 1][k] - hd[j][k];
+#else
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
       for (int k = 0; k < 3; k++) c[j][k] = v[j + 1][k + 1] + v[j][k] - v[j][k + 1] - v[j + 1][k];
+#endif
     const uint32_t m = c[1][1];
     const int code = lbp_code_of(c[0][0], c[0][1], c[0][2], c[1][2], c[2][2], c[2][1], c[2][0], c[1][0], m);
     const int idx = code >> 5;
@@ -628,11 +648,19 @@ struct PlanKey {
   unsigned iw, ih;
   float sf, mn, mx;
   int step, device;
+  int tuning;                  // the tile-planning environment hooks (tests / A-B runs flip them inside one process)
   bool operator==(const PlanKey &o) const {
     return hash == o.hash && iw == o.iw && ih == o.ih && sf == o.sf && mn == o.mn && mx == o.mx && step == o.step &&
-           device == o.device;
+           device == o.device && tuning == o.tuning;
   }
 };
+static int plan_tuning() {
+  auto geti = [](const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+  };
+  return geti("GS_B200_LBP_TILE_KB", 113) * 65536 + (geti("GS_B200_LBP_BIG", -1) + 2) * 4096 + geti("GS_B200_LBP_BIG_ROWS", 32);
+}
 struct PlanEntry {
   PlanKey key;
   void *blob = nullptr;
@@ -712,7 +740,7 @@ static PlanRef get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned ih
                         int step) {
   int dev = 0;
   cudaGetDevice(&dev);
-  PlanKey key = {cascade_hash(c), iw, ih, sf, mn, mx, step, dev};
+  PlanKey key = {cascade_hash(c), iw, ih, sf, mn, mx, step, dev, plan_tuning()};
   std::lock_guard<std::mutex> lock(g_plan_mutex);
   for (auto &r : g_plans)
     if (r->key == key) return r;
@@ -749,8 +777,13 @@ static PlanRef get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned ih
   // window tiles for k_lbp_scan3: per scale the widest tile whose box fits a TMA box (256 elements per
   // dimension) and the tallest one whose box fits the shared-memory budget
   const size_t table_bytes_t = sizeof(TileGeo) * nf + sizeof(Weak) * nw + sizeof(Stage) * nst + 4 * (size_t)nsub;
-  size_t tile_budget = (size_t)100 * 1024;
+  // per-CTA shared-memory budget (tile planes + tables + survivor lists): 113 KB lets two 512-thread CTAs share an
+  // SM at every scale (round 1 bounded the planes alone by 100 KB, and scale 10 of the UHD ladder came out at
+  // 119.9 KB: one CTA per SM, 705 us instead of ~500)
+  size_t tile_budget = (size_t)113 * 1024;
   if (const char *tb = getenv("GS_B200_LBP_TILE_KB")) tile_budget = (size_t)atoi(tb) * 1024;
+  int big_auto_rows = 32;                                            // scales whose 2-per-SM tile has fewer window rows go big
+  if (const char *br = getenv("GS_B200_LBP_BIG_ROWS")) big_auto_rows = atoi(br);
   std::vector<TileGeo> tgeo;
   bool tiles_ok = safe && ns > 0 && iw % 8 == 0 && step == 2;
   for (int s2 = 0; s2 < ns && tiles_ok; s2++) {
@@ -767,17 +800,32 @@ static PlanRef get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned ih
       break;
     }
     tp.bw = (tp.twx - 1 + (si.win_w + 7) / 2 + 1 + 3) & ~3;   // plane columns: lx + (fx + i*fw + 7) / 2
-    tp.twy = 0;
-    for (int cand = 64 * 32 / tp.twx; cand >= 1; cand /= 2) {      // at most 2048 windows (64 mask words)
-      const int ph = (cand - 1) * step + si.win_h + 1;
-      const size_t plane = ((size_t)tp.bw * ph * 4 + 127) & ~(size_t)127;
-      const size_t nwarps = LBP3_THREADS / 32, slots = (size_t)tp.twx * cand / 32;
-      const size_t total = 2 * plane + 384 + table_bytes_t + 4 * nwarps * ((slots + nwarps - 1) / nwarps) * 32 + 64;
-      if (ph <= 256 && (2 * plane <= tile_budget || cand == 1) && total <= (size_t)220 * 1024) {
-        tp.twy = cand, tp.ph = ph, tp.smem = total;
-        break;
+    // Tallest tile under a per-CTA shared-memory budget.  A window row costs 2 table rows, the first one win_h + 1:
+    // for the large scales a 113 KB CTA (two per SM) holds only 8-16 window rows -- 1 or 2 slots per warp, and a
+    // (win_h + 1)-row halo re-read per 16 rows -- so those scales run one 1024-thread CTA per SM on a tile of up to
+    // 224 KB instead (round 1: scales 10..14 of the UHD ladder took 30-60 % longer than the small ones).
+    auto fit = [&](int nthreads, size_t budget, int max_windows, TilePlan &o) {
+      o = tp;
+      o.twy = 0, o.threads = nthreads;
+      for (int cand = max_windows / tp.twx; cand >= 1; cand--) {
+        if (cand > 32 && cand % 8) continue;                       // keep the candidate list short
+        const int ph = (cand - 1) * step + si.win_h + 1;
+        const size_t plane = ((size_t)tp.bw * ph * 4 + 127) & ~(size_t)127;
+        const size_t nwarps = nthreads / 32, slots = (size_t)tp.twx * cand / 32;
+        const size_t total = 2 * plane + 640 + table_bytes_t + 4 * nwarps * ((slots + nwarps - 1) / nwarps) * 32 + 64;
+        if (ph <= 256 && (total <= budget || cand == 1) && total <= (size_t)226 * 1024) {
+          o.twy = cand, o.ph = ph, o.smem = total;
+          break;
+        }
       }
-    }
+    };
+    TilePlan small, big;
+    fit(LBP3_THREADS, tile_budget, 2048, small);
+    fit(LBP3_BIG_THREADS, (size_t)224 * 1024, 32 * LBP3_HIT_WORDS, big);
+    int big_mode = -1;                                             // -1 auto, 0 never, 1 always (A/B hook)
+    if (const char *be = getenv("GS_B200_LBP_BIG")) big_mode = atoi(be);
+    const bool use_big = big.twy > 0 && (big_mode == 1 || (big_mode < 0 && small.twy < big_auto_rows));
+    tp = use_big ? big : small;
     if (!tp.twy) {
       tiles_ok = false;
       break;
@@ -912,7 +960,8 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
   if (v3) {
     static gsb::DeviceOnce once3;
     if (once3.needed()) {
-      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan3, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan3<gsb::LBP3_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      GSB_CHECK(cudaFuncSetAttribute(gsb::k_lbp_scan3<gsb::LBP3_BIG_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
       once3.done();
     }
     GSB_CHECK(cudaMemsetAsync(masks, 0, 4 * (size_t)dc.total_slots * n, st));   // padding slots between scales
@@ -936,8 +985,12 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
         CUtensorMap tm;
         if (!gsb::make_tmap_u32frames(&tm, planes, iw / 2, ih, 2 * nf, (unsigned)tp.bw, (unsigned)tp.ph))
           return gsb::record_error(cudaErrorInvalidValue, __FILE__, __LINE__);
-        gsb::k_lbp_scan3<<<dim3((unsigned)(tp.tiles_x * tp.tiles_y), nf), gsb::LBP3_THREADS, tp.smem, st>>>(
-            tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, masks + (size_t)f0 * dc.total_slots);
+        if (tp.threads == gsb::LBP3_BIG_THREADS)
+          gsb::k_lbp_scan3<gsb::LBP3_BIG_THREADS><<<dim3((unsigned)(tp.tiles_x * tp.tiles_y), nf), gsb::LBP3_BIG_THREADS, tp.smem, st>>>(
+              tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, masks + (size_t)f0 * dc.total_slots);
+        else
+          gsb::k_lbp_scan3<gsb::LBP3_THREADS><<<dim3((unsigned)(tp.tiles_x * tp.tiles_y), nf), gsb::LBP3_THREADS, tp.smem, st>>>(
+              tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, masks + (size_t)f0 * dc.total_slots);
         GSB_LAUNCHED(1);
       }
     }

@@ -206,7 +206,7 @@ def test_integral_single_pass_batches(G, O, kernel):
         os.environ["GS_B200_INTEGRAL"] = kernel
     try:
         for (w, h, n) in ((3840, 2160, 40), (256, 37, 33), (4096, 100, 40), (8192, 33, 32), (1920, 1080, 80), (8, 16, 160), (40, 17, 150),
-                          (1032, 9, 75), (2048, 8, 74), (5000 // 8 * 8, 23, 40)):
+                          (1032, 9, 75), (2048, 8, 74), (5000 // 8 * 8, 23, 40), (2048, 19, 300)):
             rng = np.random.default_rng(w + h)
             fr = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
             fr[n - 1] = 255
@@ -921,3 +921,23 @@ def test_blobs_corners_perspective_vs_reference_goldens_and_oracle(G, O):
         want = np.empty((70, 90), np.uint8)
         O.gso_perspective_correct(L.ptr(want), 90, 70, L.ptr(frames[i]), 200, 150, L.ptr(np.ascontiguousarray(quads[i].astype(np.uint32))))
         assert np.array_equal(out[i], want), i
+
+
+@pytest.mark.parametrize("big", ["0", "1"])
+def test_lbp_tile_configs(G, O, cas, big):
+    """k_lbp_scan3 runs a scale either as two 512-thread CTAs per SM or (large windows) as one 1024-thread CTA with a
+    tile of up to 224 KB; GS_B200_LBP_BIG forces one form for every scale.  Both against the oracle on frames wide and
+    tall enough for several tiles per scale, all 15 scales of the 1.1 ladder"""
+    w, h = 704, 520
+    frames = np.stack([L.natural_like(w, h, 80 + i) for i in range(2)])
+    ii = np.stack([o_integral(O, f) for f in frames])
+    os.environ["GS_B200_LBP_BIG"] = big
+    try:
+        rects, counts = G.lbp_detect_batch(cas, dev(ii.view(np.int32)), 4000, 1.1, 1.0, 4.0, 2)
+        got = G.rects_to_numpy(rects, counts)
+    finally:
+        del os.environ["GS_B200_LBP_BIG"]
+    for i in range(2):
+        want = o_detect(O, cas, ii[i], 4000, 1.1, 1.0, 4.0, 2)
+        assert got[i].tobytes() == want.tobytes(), (big, i, len(got[i]), len(want))
+        assert len(want) > 3

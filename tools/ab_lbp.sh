@@ -1,12 +1,9 @@
 #!/bin/bash
-# A/B the LBP scan variants (GS_B200_LIB selects the library)
-for v in "$@"; do
-  export GS_B200_LIB=$PWD/grayskull_b200/$v.so
-  ok=$(timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 300 -k "lbp_vs or c4" 2>&1 | tail -1)
-  timeout 300 python bench.py --workload c4 --steps 3 --warmup 1 --batch 32 --no-cpu > gpurun_out/ab_$v.json 2>gpurun_out/ab.err
-  python - <<PY
-import json
-d=json.load(open("gpurun_out/ab_$v.json"))
-print("%-20s %.3e windows/s  lbp %.2f ms | tests: $ok" % ("$v", d["value"], d["kernels"]["gs_lbp_detect"]["ms"]))
-PY
-done
+# LBP A/B on 32 UHD frames (c4 workload): which scales run the 1024-thread / 224 KB tile form
+c4() { timeout 300 python bench.py --workload c4 --steps 3 --warmup 1 --batch 32 --no-cpu 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('%-22s c4 %.3e windows/s  lbp %.2f ms' % ('$1', d['value'], d['kernels']['gs_lbp_detect']['ms']))"; }
+c4 auto_rows32
+GS_B200_LBP_BIG=0 c4 big_never
+GS_B200_LBP_BIG=1 c4 big_always
+GS_B200_LBP_BIG_ROWS=17 c4 auto_rows17
+GS_B200_LBP_BIG_ROWS=9 c4 auto_rows9
