@@ -445,7 +445,7 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
            int strips, int cparam, float minv, int fast_ok) {
   // prefix row of a warp, transposed: P(8 l + k) lives at [k][16 + l], so that for a fixed register index k the 32
   // lanes touch 32 consecutive words (the natural [8 l + k] layout is an 8-way bank conflict on every read)
-  __shared__ uint32_t sp_all[4][2][8][64];
+  __shared__ uint32_t sp_all[4][8][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = (int)blockIdx.x * 4 + warp;
   if (strip >= strips) return;                                  // warp-uniform; no CTA barriers below
@@ -490,15 +490,15 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
   const uint8_t *p_cen = frame + (ptrdiff_t)(yb + 1) * w + x0;
   uint8_t *qo = out + (size_t)yb * w + x0;
   // word offsets of P(i + r) and P(i - r - 1) in the transposed prefix row, for this lane's 8 pixels (row invariant)
-  int offA[8], offB[8];
+  const uint32_t *pA[8], *pB[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int ca = k + r, cb = k - r - 1 + 128;                // cb biased by 16 lanes: >= 0
-    offA[k] = (ca & 7) * 64 + 16 + lane + (ca >> 3);
-    offB[k] = (cb & 7) * 64 + lane + (cb >> 3);
+    pA[k] = &sp[0][0] + (ca & 7) * 64 + 16 + lane + (ca >> 3);
+    pB[k] = &sp[0][0] + (cb & 7) * 64 + lane + (cb >> 3);
   }
-  uint32_t (*sp0)[64] = sp_all[warp][0], (*sp1)[64] = sp_all[warp][1];
-  if (lane == 0) sp0[7][15] = 0u, sp1[7][15] = 0u;              // P(-1) = 0
+  uint32_t (*sp)[64] = sp_all[warp];
+  if (lane == 0) sp[7][15] = 0u;                                // P(-1) = 0
   __syncwarp();
 
   for (int y = yb; y < ye; y++) {
@@ -519,15 +519,14 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
       if (lane >= o) incl += t;
     }
     const uint32_t excl = incl - p[7];
-    uint32_t (*sp)[64] = ((y - yb) & 1) ? sp1 : sp0;
+    __syncwarp();                                                 // the previous row's reads are done
 #pragma unroll
     for (int k = 0; k < 8; k++) sp[k][16 + lane] = p[k] + excl;
     __syncwarp();
     if (out_lane) {
       uint32_t W[8];
-      const uint32_t *spf = &sp[0][0];
 #pragma unroll
-      for (int k = 0; k < 8; k++) W[k] = spf[offA[k]] - spf[offB[k]];
+      for (int k = 0; k < 8; k++) W[k] = *pA[k] - *pB[k];
       const int ch = min(y + r, h - 1) - max(y - r, 0) + 1;
       uint32_t q[8];
       if (fast_ok && cols_full && ch == FULL) {

@@ -14,9 +14,11 @@ C5 = dict(radius=5, nkps=1250, threshold=20, max_rects=4096, scale_factor=1.1, m
 
 
 class FramePipeline:
-    """Preallocated C5 chain for up to `n` frames of h x w on `device`."""
+    """Preallocated C5 chain for up to `n` frames of h x w on `device`.  fused=True runs blur -> sobel as the one-pass
+    gs_b200_blur_sobel_batch (no blurred intermediate: n*h*w bytes less memory and half the HBM traffic of the pair,
+    but instruction-bound and ~15 % slower than the two kernels on B200, so it is not the default)."""
 
-    def __init__(self, cascade, n, h, w, device, fused=True, **params):
+    def __init__(self, cascade, n, h, w, device, fused=False, **params):
         import torch
         self.p = dict(C5)
         self.p.update(params)
