@@ -490,6 +490,9 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
   const uint8_t *p_cen = frame + (ptrdiff_t)(yb + 1) * w + x0;
   uint8_t *qo = out + (size_t)yb * w + x0;
   // word offsets of P(i + r) and P(i - r - 1) in the transposed prefix row, for this lane's 8 pixels (row invariant)
+  uint32_t (*sp)[64] = sp_all[warp];
+  if (lane == 0) sp[7][15] = 0u;                                // P(-1) = 0
+  __syncwarp();
   const uint32_t *pA[8], *pB[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -497,9 +500,6 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
     pA[k] = &sp[0][0] + (ca & 7) * 64 + 16 + lane + (ca >> 3);
     pB[k] = &sp[0][0] + (cb & 7) * 64 + lane + (cb >> 3);
   }
-  uint32_t (*sp)[64] = sp_all[warp];
-  if (lane == 0) sp[7][15] = 0u;                                // P(-1) = 0
-  __syncwarp();
 
   for (int y = yb; y < ye; y++) {
     const uint2 en2 = ldp(p_en, y + r + 2), lv2 = ldp(p_lv, y + 1 - r);

@@ -923,12 +923,23 @@ k_orb_brief(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__re
   } else {
     uint8_t *patch = s_patch[warp];
     const int xa = (x - BP_R) & ~3;                      // patch byte 0 <-> image column xa (w % 4 == 0)
-    for (int i = lane; i < BP_ROWS * (BP_PITCH / 4); i += 32) {
+    // all 17 word loads of a lane are issued before the first store (the rolled loop waited for each load in turn:
+    // 53 % of the kernel's stall samples sat on its STS, profiles/r01_ncu_orb_brief_detail.txt)
+    constexpr int BP_WORDS = BP_ROWS * (BP_PITCH / 4), BP_ITERS = (BP_WORDS + 31) / 32;
+    uint32_t pv[BP_ITERS];
+#pragma unroll
+    for (int k = 0; k < BP_ITERS; k++) {
+      const int i = (int)lane + 32 * k;
       const int r = i / (BP_PITCH / 4), c = i % (BP_PITCH / 4);
       const int yy = y - BP_R + r, xx = xa + 4 * c;
-      uint32_t v = 0;
-      if (yy >= 0 && yy < (int)h && xx >= 0 && xx < (int)w) v = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)yy * w + xx));
-      reinterpret_cast<uint32_t *>(patch)[i] = v;
+      pv[k] = 0;
+      if (i < BP_WORDS && yy >= 0 && yy < (int)h && xx >= 0 && xx < (int)w)
+        pv[k] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)yy * w + xx));
+    }
+#pragma unroll
+    for (int k = 0; k < BP_ITERS; k++) {
+      const int i = (int)lane + 32 * k;
+      if (i < BP_WORDS) reinterpret_cast<uint32_t *>(patch)[i] = pv[k];
     }
     __syncwarp();
     const int ox = x - xa;                               // keypoint column inside the patch

@@ -181,24 +181,10 @@ k_lbp_scan(const uint32_t *__restrict__ ii_all, unsigned iw, unsigned ih, DevCas
 #ifndef GSB_LBP_FSHIFT
 #define GSB_LBP_FSHIFT 0
 #endif
-#ifndef GSB_LBP_CARRY
-#define GSB_LBP_CARRY 0
-#endif
-#ifndef GSB_LBP_GW
-#define GSB_LBP_GW 1                          // warps that pool their survivor lists (1 = warp-private lists)
-#endif
+
 __device__ __forceinline__ int lbp_code_of(uint32_t n7, uint32_t n6, uint32_t n5, uint32_t n4, uint32_t n3, uint32_t n2,
                                            uint32_t n1, uint32_t n0, uint32_t m) {
-#if GSB_LBP_CARRY
-  // `cell >= centre` as the borrow of cell - centre, shifted into the code word by an add-with-carry:
-  // IADD3 (carry out) + IADD3.X per bit instead of compare + select + or
-  uint32_t acc = 0;
-#define GSB_LBP_BIT(n) asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(acc) : "r"(n), "r"(m))
-  GSB_LBP_BIT(n7); GSB_LBP_BIT(n6); GSB_LBP_BIT(n5); GSB_LBP_BIT(n4);
-  GSB_LBP_BIT(n3); GSB_LBP_BIT(n2); GSB_LBP_BIT(n1); GSB_LBP_BIT(n0);
-#undef GSB_LBP_BIT
-  return (int)(~acc & 0xFFu);      // acc collected the borrows (cell < centre)
-#elif GSB_LBP_FSHIFT
+#if GSB_LBP_FSHIFT
   // EXPERIMENT (not measured yet, off by default): cell sums are far below 2^31, so `cell >= centre` is the
   // inverted sign of cell - centre; a funnel shift appends that sign to the code word: 2 instructions per bit
   // instead of compare + select + or.
@@ -421,7 +407,7 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
   unsigned char *ctl = lsm + ((tile_bytes + 127u) & ~127u);
   uint64_t &bar = *reinterpret_cast<uint64_t *>(ctl);
   unsigned *hit = reinterpret_cast<unsigned *>(ctl + 16);   // twy * (twx / 32) <= LBP3_HIT_WORDS mask words
-  TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 1024);   // ctl + 640 .. 1024: group counters
+  TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 640);
   Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
   Stage *s_stage = reinterpret_cast<Stage *>(s_weak + dc.nweaks);
   int *s_sub = reinterpret_cast<int *>(s_stage + dc.nstages);
@@ -504,110 +490,6 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     }
     return true;
   };
-#if GSB_LBP_GW > 1
-  // GSB_LBP_GW > 1: survivors are pooled per GROUP of GW warps (named barrier among GW * 32 threads) instead of per
-  // warp: a warp-private list of <= 128 windows leaves the last iteration of every stage group mostly empty (ncu:
-  // 24 of 32 lanes active); a group list is GW times longer, at the price of one GW-warp barrier per stage group.
-  constexpr int NWARPS = LBP3_THREADS / 32;
-  constexpr int GW = GSB_LBP_GW, NG = NWARPS / GW;
-  const unsigned warp = tid >> 5, lt = (1u << lane) - 1u;
-  const unsigned gidx = warp / GW, wig = warp % GW, gtid = tid % (GW * 32);
-  const int nslots = nwin >> 5;
-  const int gcap = ((nslots + NG - 1) / NG) * 32;
-  uint16_t *cur = list_a + gidx * gcap, *nxt = list_a + (NG + gidx) * gcap;
-  unsigned *gcnt = reinterpret_cast<unsigned *>(ctl + 640) + gidx * LBP_MAX_GROUPS;   // zeroed below, one counter per stage group
-  auto group_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(gidx + 1), "r"(GW * 32) : "memory"); };
-  if (gtid < LBP_MAX_GROUPS) gcnt[gtid] = 0;
-  group_bar();
-  {
-    const bool last = dc.ngroups == 1;
-    for (int slot = (int)gidx + (int)wig * NG; slot < nslots; slot += GW * NG) {
-      const unsigned id = (unsigned)slot * 32u + lane;
-      const int lx = (int)(id & (unsigned)(twx - 1)), ly = (int)(id >> shift);
-      const bool valid = wx0 + lx < sc.nx && wy0 + ly < sc.ny;
-      const bool alive = valid && run(id, 0, dc.group_end[0]);
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
-      if (last) {
-        if (lane == 0 && bal) hit[slot] = bal;               // bit = lane = lx % 32
-      } else if (bal) {
-        unsigned pos = 0;
-        if (lane == 0) pos = atomicAdd(&gcnt[0], __popc(bal));
-        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        if (alive) cur[pos + __popc(bal & lt)] = (uint16_t)id;
-      }
-    }
-  }
-  group_bar();
-  for (int g = 1; g < dc.ngroups; g++) {
-    unsigned n = gcnt[g - 1];
-    if (n == 0) break;
-    if (n <= (unsigned)flat_n) {
-      // few survivors in the whole group: one warp finishes them in the flat (window, weak) mode
-      if (wig == 0) {
-        for (int sgi = dc.group_end[g - 1]; sgi < dc.nstages && n; sgi++) {
-          const Stage st = s_stage[sgi];
-          const bool last = sgi == dc.nstages - 1;
-          int P = 1;
-          while (P < (int)st.n && P < 32) P <<= 1;
-          const unsigned wpw = 32u / (unsigned)P;
-          const unsigned seg = lane & ~(unsigned)(P - 1), li = lane & (unsigned)(P - 1);
-          unsigned m = 0;
-          for (unsigned b0 = 0; b0 < n; b0 += wpw) {
-            const unsigned w = b0 + lane / (unsigned)P;
-            const unsigned id = w < n ? cur[w] : 0;
-            float sum = 0.0f;
-            for (int c0 = 0; c0 < (int)st.n; c0 += P) {
-              const int wi = c0 + (int)li;
-              const float val = (w < n && wi < (int)st.n) ? vote(id, s_weak[st.start + wi]) : 0.0f;
-              const int mm = min(P, (int)st.n - c0);
-              for (int i = 0; i < mm; i++) sum = __fadd_rn(sum, __shfl_sync(0xFFFFFFFFu, val, (int)seg + i));
-            }
-            const bool alive = w < n && li == 0 && !(sum < st.thr);
-            const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
-            if (last) {
-              if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));
-            } else {
-              if (alive) nxt[m + __popc(bal & lt)] = (uint16_t)id;
-              m += __popc(bal);
-            }
-          }
-          __syncwarp();
-          n = last ? 0 : m;
-          uint16_t *t = cur;
-          cur = nxt, nxt = t;
-        }
-      }
-      break;
-    }
-    const bool last = g == dc.ngroups - 1;
-    for (unsigned i0 = wig * 32; i0 < n; i0 += GW * 32) {
-      const unsigned i = i0 + lane;
-      const unsigned id = i < n ? cur[i] : 0;
-      const bool alive = i < n && run(id, dc.group_end[g - 1], dc.group_end[g]);
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, alive);
-      if (last) {
-        if (alive) atomicOr(&hit[id >> 5], 1u << (id & 31));
-      } else if (bal) {
-        unsigned pos = 0;
-        if (lane == 0) pos = atomicAdd(&gcnt[g], __popc(bal));
-        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-        if (alive) nxt[pos + __popc(bal & lt)] = (uint16_t)id;
-      }
-    }
-    group_bar();
-    uint16_t *t = cur;
-    cur = nxt, nxt = t;
-  }
-  // the group's slots were touched by nobody else: store their mask words and leave -- no CTA barrier
-  group_bar();
-  const int sx_n = twx >> 5;
-  for (int slot = (int)gidx + (int)gtid * NG; slot < nslots; slot += GW * 32 * NG) {
-    const int ly = slot / sx_n, sx = slot % sx_n;
-    const unsigned chunk = (unsigned)(wx0 >> 5) + (unsigned)sx;
-    if (wy0 + ly < sc.ny && chunk < sc.chunks)
-      masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[slot];
-  }
-#else
   // From here on every warp works alone on its own 32-window slots (slot = warp, warp + nwarps, ...): its
   // survivors are re-packed into a warp-private list with ballots -- no shared counters, no CTA barrier until
   // the masks are written -- so a warp that is stuck in a deep stage never holds the other fifteen up.
@@ -701,7 +583,6 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     if (wy0 + ly < sc.ny && chunk < sc.chunks)
       masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[slot];
   }
-#endif
 }
 
 // hits per 8-slot block, for the ordered-compaction scan
@@ -932,7 +813,7 @@ static PlanRef get_plan(const struct gs_lbp_cascade *c, unsigned iw, unsigned ih
         const int ph = (cand - 1) * step + si.win_h + 1;
         const size_t plane = ((size_t)tp.bw * ph * 4 + 127) & ~(size_t)127;
         const size_t nwarps = nthreads / 32, slots = (size_t)tp.twx * cand / 32;
-        const size_t total = 2 * plane + 1024 + table_bytes_t + 4 * nwarps * ((slots + nwarps - 1) / nwarps) * 32 + 64;
+        const size_t total = 2 * plane + 640 + table_bytes_t + 4 * nwarps * ((slots + nwarps - 1) / nwarps) * 32 + 64;
         if (ph <= 256 && (total <= budget || cand == 1) && total <= (size_t)226 * 1024) {
           o.twy = cand, o.ph = ph, o.smem = total;
           break;

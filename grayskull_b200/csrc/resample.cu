@@ -66,9 +66,7 @@ constexpr int RS_ROWS = 8;
 #ifndef GSB_RS_PIPE
 #define GSB_RS_PIPE 0
 #endif
-#ifndef GSB_RS_F2
-#define GSB_RS_F2 0
-#endif
+
 
 __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c11, float omx, float dx, float omy,
                                         float dy) {
@@ -82,36 +80,6 @@ __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c
 // dst pixel capped round 1's kernel at ~4 pixels/clk/SM): 0x4B0000bb is the float 2^23 + bb, so one PRMT (ALU pipe)
 // and one exact FADD (FMA pipe) give float(bb); adding 2^23 to p in [0, 256) with round-toward-zero leaves
 // trunc(p) in the low byte.
-// Packed fp32x2 (Blackwell FFMA2): two pixels per issue slot.  Only the fused form exists in hardware, and ptxas turns a
-// mul.rn.f32x2 followed by an add.rn.f32x2 into ONE FFMA2 (single rounding) even under -fmad=false, so every step is
-// written as an explicit fma: a * b + (-0) is mul.rn's result bit for bit, a * 1 + c is add.rn's.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 mk2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void un2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { return fma2(a, b, 0x8000000080000000ull); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { return fma2(a, 0x3F8000003F800000ull, b); }
-// two bilerps at once (reference :181-184, left to right), the same y weights for both
-__device__ __forceinline__ f32x2 bilerp2(f32x2 c00, f32x2 c01, f32x2 c10, f32x2 c11, f32x2 omx, f32x2 dx, f32x2 omy, f32x2 dy) {
-  f32x2 p = mul2(mul2(c00, omx), omy);
-  p = add2(p, mul2(mul2(c01, dx), omy));
-  p = add2(p, mul2(mul2(c10, omx), dy));
-  p = add2(p, mul2(mul2(c11, dx), dy));
-  return p;
-}
-// two u8 -> f32 conversions: (0x4B0000aa, 0x4B0000bb) - (2^23, 2^23), one FFMA2
-__device__ __forceinline__ f32x2 bytes2_f(uint32_t ma, uint32_t mb) {
-  return fma2(mk2(__uint_as_float(ma), __uint_as_float(mb)), 0x3F8000003F800000ull, 0xCB000000CB000000ull);
-}
-
 __device__ __forceinline__ float byte_f(uint32_t w, int k) {
   return __fsub_rn(__uint_as_float(prmt(w, 0x4B000000u, 0x7540u | (unsigned)k)), 8388608.0f);
 }
@@ -188,47 +156,18 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
       uint32_t out = 0;
       if (pairs) {
         const uint2 a = __ldg(reinterpret_cast<const uint2 *>(r0 + x0[0])), b = __ldg(reinterpret_cast<const uint2 *>(r1 + x0[0]));
-#if GSB_RS_F2
-        const uint32_t M = 0x4B000000u;
-        const f32x2 omy2 = mk2(omy, omy), dy2 = mk2(dy, dy);
-        // pixels (0, 1) from the low words, (2, 3) from the high words
-        const f32x2 q01 = bilerp2(bytes2_f(prmt(a.x, M, 0x7540), prmt(a.x, M, 0x7542)), bytes2_f(prmt(a.x, M, 0x7541), prmt(a.x, M, 0x7543)),
-                                  bytes2_f(prmt(b.x, M, 0x7540), prmt(b.x, M, 0x7542)), bytes2_f(prmt(b.x, M, 0x7541), prmt(b.x, M, 0x7543)),
-                                  mk2(omx[0], omx[1]), mk2(dx[0], dx[1]), omy2, dy2);
-        const f32x2 q23 = bilerp2(bytes2_f(prmt(a.y, M, 0x7540), prmt(a.y, M, 0x7542)), bytes2_f(prmt(a.y, M, 0x7541), prmt(a.y, M, 0x7543)),
-                                  bytes2_f(prmt(b.y, M, 0x7540), prmt(b.y, M, 0x7542)), bytes2_f(prmt(b.y, M, 0x7541), prmt(b.y, M, 0x7543)),
-                                  mk2(omx[2], omx[3]), mk2(dx[2], dx[3]), omy2, dy2);
-        float p0, p1, p2, p3;
-        un2(q01, p0, p1);
-        un2(q23, p2, p3);
-#else
         const float p0 = bilerp(byte_f(a.x, 0), byte_f(a.x, 1), byte_f(b.x, 0), byte_f(b.x, 1), omx[0], dx[0], omy, dy);
         const float p1 = bilerp(byte_f(a.x, 2), byte_f(a.x, 3), byte_f(b.x, 2), byte_f(b.x, 3), omx[1], dx[1], omy, dy);
         const float p2 = bilerp(byte_f(a.y, 0), byte_f(a.y, 1), byte_f(b.y, 0), byte_f(b.y, 1), omx[2], dx[2], omy, dy);
         const float p3 = bilerp(byte_f(a.y, 2), byte_f(a.y, 3), byte_f(b.y, 2), byte_f(b.y, 3), omx[3], dx[3], omy, dy);
-#endif
         out = prmt(prmt(f_trunc_bits(p0), f_trunc_bits(p1), 0x0040), prmt(f_trunc_bits(p2), f_trunc_bits(p3), 0x0040), 0x5410);
       } else {
-#if GSB_RS_F2
-        const uint32_t M = 0x4B000000u;
-        const f32x2 omy2 = mk2(omy, omy), dy2 = mk2(dy, dy);
-#pragma unroll
-        for (int j = 0; j < 4; j += 2) {
-          const f32x2 c00 = bytes2_f(__ldg(r0 + x0[j]) | M, __ldg(r0 + x0[j + 1]) | M), c01 = bytes2_f(__ldg(r0 + x1[j]) | M, __ldg(r0 + x1[j + 1]) | M);
-          const f32x2 c10 = bytes2_f(__ldg(r1 + x0[j]) | M, __ldg(r1 + x0[j + 1]) | M), c11 = bytes2_f(__ldg(r1 + x1[j]) | M, __ldg(r1 + x1[j + 1]) | M);
-          float pa, pb;
-          un2(bilerp2(c00, c01, c10, c11, mk2(omx[j], omx[j + 1]), mk2(dx[j], dx[j + 1]), omy2, dy2), pa, pb);
-          out |= (f_trunc_bits(pa) & 0xFFu) << (8 * j);
-          out |= (f_trunc_bits(pb) & 0xFFu) << (8 * j + 8);
-        }
-#else
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const float c00 = u8_f(__ldg(r0 + x0[j])), c01 = u8_f(__ldg(r0 + x1[j]));
           const float c10 = u8_f(__ldg(r1 + x0[j])), c11 = u8_f(__ldg(r1 + x1[j]));
           out |= (f_trunc_bits(bilerp(c00, c01, c10, c11, omx[j], dx[j], omy, dy)) & 0xFFu) << (8 * j);
         }
-#endif
       }
       uint8_t *q = d + (size_t)y * dw + x;
       if (VEC) {
