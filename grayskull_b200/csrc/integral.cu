@@ -80,7 +80,7 @@ constexpr int IB_BH = 16;   // rows per band
 template <int MAXT>   // block-size bound; per-row thread offsets live in shared memory to stay <= 64 registers
 __global__ void __launch_bounds__(MAXT, 1024 / MAXT)
 k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, unsigned w, unsigned h, unsigned n,
-                 unsigned nbands, unsigned *__restrict__ ctrl, uint32_t *__restrict__ agg) {
+                 unsigned nbands, unsigned *__restrict__ ctrl) {
   __shared__ uint32_t wtot[IB_BH][32];   // per-row warp totals
   __shared__ unsigned s_ticket;
   extern __shared__ uint32_t s_off[];    // [IB_BH][blockDim.x]: exclusive horizontal offset of each thread, per row
@@ -132,51 +132,8 @@ k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, uns
   __syncthreads();
 
   // ---- the row above the band -----------------------------------------------------------------
-  // [r2] decoupled look-back (agg != nullptr).  Round 1 waited for the band above to publish its FINAL last row,
-  // which that band could only do after receiving its own top row: a serial chain through the bands of a frame
-  // that are in flight together (ncu: 35 % of the stall samples on the flag spin).  Now a band first publishes its
-  // AGGREGATE row (its last row without any top: band-local, no dependency; flag = 1) and a successor adds up
-  // aggregates downwards until it meets a band whose final row is out (flag = 2): nobody waits for more than a
-  // neighbour's band-local phase.
   uint32_t top[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  __shared__ unsigned s_flag;
-  if (agg != nullptr) {
-    if (band + 1 < nbands) {                     // the last band of a frame has no successor
-      if (live) {
-        const int last = (int)rows - 1;
-        uint32_t o[8];
-        uint32_t run = s_off[last * blockDim.x + tid] + wtot[last][warp];
-#pragma unroll
-        for (int c = 0; c < 8; c++) run += acc[c], o[c] = run;
-        uint4 *q = reinterpret_cast<uint4 *>(agg + ((size_t)frame * nbands + band) * w + x);
-        q[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        q[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) *(volatile unsigned *)(ctrl + 1 + (size_t)frame * nbands + band) = 1u;
-    }
-    for (int pb = (int)band - 1; pb >= 0; pb--) {
-      if (tid == 0) {
-        volatile unsigned *flag = ctrl + 1 + (size_t)frame * nbands + pb;
-        unsigned f;
-        while ((f = *flag) == 0) __nanosleep(20);
-        __threadfence();
-        s_flag = f;
-      }
-      __syncthreads();
-      const unsigned f = s_flag;
-      if (live) {
-        // final row of band pb = the table's own row; aggregate = the scratch row
-        const uint32_t *rowp = (f == 2u) ? ii + (size_t)frame * w * h + ((size_t)(pb + 1) * IB_BH - 1) * w + x
-                                         : agg + ((size_t)frame * nbands + pb) * w + x;
-        const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(rowp)), b = __ldcg(reinterpret_cast<const uint4 *>(rowp) + 1);
-        top[0] += a.x, top[1] += a.y, top[2] += a.z, top[3] += a.w, top[4] += b.x, top[5] += b.y, top[6] += b.z, top[7] += b.w;
-      }
-      __syncthreads();                            // s_flag is rewritten by the next step
-      if (f == 2u) break;
-    }
-  } else if (band > 0) {
+  if (band > 0) {
     if (tid == 0) {
       volatile unsigned *flag = ctrl + 1 + (size_t)frame * nbands + (band - 1);
       while (*flag == 0) __nanosleep(40);
@@ -212,7 +169,7 @@ k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, uns
   __syncthreads();
   if (tid == 0) {
     volatile unsigned *flag = ctrl + 1 + (size_t)frame * nbands + band;
-    *flag = agg != nullptr ? 2u : 1u;
+    *flag = 1u;
   }
   // remaining rows
   if (live) {
@@ -398,14 +355,9 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
   if (n >= 32 && w % 8 == 0 && w <= 8192 && aligned && !gsb::force_generic() &&
       (unsigned long long)n * ((h + gsb::IB_BH - 1) / gsb::IB_BH) < 0x7FFFFFFFull) {
     const unsigned nbands = (h + gsb::IB_BH - 1) / gsb::IB_BH;
-    const size_t ctrl_bytes = (sizeof(unsigned) * (1 + (size_t)n * nbands) + 255) & ~(size_t)255;
-    const char *envb = getenv("GS_B200_INTEGRAL");      // "bands" = round 1's chain, "lookback" (default) = aggregates
-    const bool lookback = !(envb && envb[0] == 'b');
-    const size_t agg_bytes = lookback ? sizeof(uint32_t) * (size_t)n * nbands * w : 0;
-    unsigned char *wsb = static_cast<unsigned char *>(gsb::workspace(st, gsb::WS_INTEGRAL, ctrl_bytes + agg_bytes));
-    if (!wsb) return (int)cudaErrorMemoryAllocation;
-    unsigned *ctrl = reinterpret_cast<unsigned *>(wsb);
-    uint32_t *agg = lookback ? reinterpret_cast<uint32_t *>(wsb + ctrl_bytes) : nullptr;
+    const size_t ctrl_bytes = sizeof(unsigned) * (1 + (size_t)n * nbands);
+    unsigned *ctrl = static_cast<unsigned *>(gsb::workspace(st, gsb::WS_INTEGRAL, ctrl_bytes));
+    if (!ctrl) return (int)cudaErrorMemoryAllocation;
     GSB_CHECK(cudaMemsetAsync(ctrl, 0, ctrl_bytes, st));
     const unsigned threads = ((w / 8 + 31) / 32) * 32;
     const size_t smem = sizeof(uint32_t) * gsb::IB_BH * threads;   // <= 64 KB
@@ -415,8 +367,8 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
       GSB_CHECK(cudaFuncSetAttribute(gsb::k_integral_bands<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
       once.done();
     }
-    if (threads <= 512) gsb::k_integral_bands<512><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl, agg);
-    else gsb::k_integral_bands<1024><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl, agg);
+    if (threads <= 512) gsb::k_integral_bands<512><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl);
+    else gsb::k_integral_bands<1024><<<n * nbands, threads, smem, st>>>(ii, src, w, h, n, nbands, ctrl);
     GSB_LAUNCHED(1);
     return 0;
   }

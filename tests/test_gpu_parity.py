@@ -197,11 +197,10 @@ def test_stencils_vs_oracle(G, O, force_generic):
         g.lib().gs_b200_force_generic(0)
 
 
-@pytest.mark.parametrize("kernel", ["bands", "lookback", "strips", "auto"])
+@pytest.mark.parametrize("kernel", ["bands", "strips", "auto"])
 def test_integral_single_pass_batches(G, O, kernel):
-    """the single-pass kernels of integral.cu -- 16-row bands chained through the final row ("bands", round 1) or
-    through decoupled aggregates ("lookback", round 2's default) and 1024-column strips walking down the frame
-    ("strips"; the default once n * strips >= 592) -- on ragged heights, 1..8 strips per row (strip
+    """the two single-pass kernels of integral.cu -- chained 16-row bands (round 1) and 1024-column strips walking
+    down the frame (round 2; the default once n * strips >= 148) -- on ragged heights, 1..8 strips per row (strip
     seams at multiples of 1024 columns), band counts from 1 to 270, all-255 frames (the largest sums)"""
     if kernel != "auto":
         os.environ["GS_B200_INTEGRAL"] = kernel
