@@ -122,10 +122,14 @@ void gs_adaptive_threshold(struct gs_image dst, struct gs_image src, unsigned ra
 void gs_sobel(struct gs_image dst, struct gs_image src) {
   GSB_ASSERT(gs_ok(dst) && gs_ok(src) && dst.w == src.w && dst.h == src.h);  // reference :307
   const size_t n = (size_t)src.w * src.h;
-  // dst is copied in as well: its 1-px frame must keep the caller's bytes (reference :308-309)
-  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, true);
+  if (src.w < 3 || src.h < 3) return;      // nothing is written (reference :308-309)
+  // dst's 1-px frame must keep the caller's bytes (reference :308-309): a staged dst is not copied in at all,
+  // only the interior (w-2) x (h-2) block travels back, as one strided copy
+  Buf s = in_buf(src.data, n, gsb::WS_STAGE_A), d = in_buf(dst.data, n, gsb::WS_STAGE_B, false);
   GS_DO(gs_b200_sobel_batch((uint8_t *)d.dev, (const uint8_t *)s.dev, src.w, src.h, 1, S()));
-  out_buf(d);
+  if (d.host)
+    GS_CUDA(cudaMemcpy2DAsync((uint8_t *)d.host + src.w + 1, src.w, (const uint8_t *)d.dev + src.w + 1, src.w, src.w - 2,
+                              src.h - 2, cudaMemcpyDeviceToHost, S()));
   finish();
 }
 

@@ -49,6 +49,9 @@ constexpr int BX_RMAX = 7;
 #ifndef GSB_BX_LO_XU
 #define GSB_BX_LO_XU 1                     // 1: low lane too
 #endif
+#ifndef GSB_BX_RING
+#define GSB_BX_RING 0
+#endif
 #ifndef GSB_BX_TOT_IMAD
 #define GSB_BX_TOT_IMAD 1                   // 1: lane totals by IMAD x 0x10001 instead of PRMT + add
 #endif
@@ -240,12 +243,22 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
   if (yb >= (int)h) return;                    // warp-uniform
 
   uint32_t S[4] = {0, 0, 0, 0};                // column sums of the 2R rows above the next window row
+#if GSB_BX_RING
+  // interior tiles (fully unrolled walk): the unpacked pair words of the 2R+1 rows in the window stay in a register
+  // ring, so the row that leaves is not loaded and unpacked a second time (one LDS.64 + four PRMT per row step)
+  uint32_t ring[2 * R + 1][4];
+#endif
 #pragma unroll
   for (int i = 0; i < 2 * R; i++) {
     uint32_t e[4];
     unpack_pairs(*reinterpret_cast<const uint2 *>(in + i * BX_PW), e);
 #pragma unroll
-    for (int k = 0; k < 4; k++) S[k] += e[k];
+    for (int k = 0; k < 4; k++) {
+      S[k] += e[k];
+#if GSB_BX_RING
+      ring[i][k] = e[k];
+#endif
+    }
   }
   uint32_t L[4] = {0, 0, 0, 0};                // the row that leaves the window at this step
 
@@ -255,6 +268,15 @@ k_box_tma(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, u
     unpack_pairs(*reinterpret_cast<const uint2 *>(in + (i + 2 * R) * BX_PW), e);
 #pragma unroll
     for (int k = 0; k < 4; k++) S[k] = S[k] + e[k] - L[k];   // one IADD3 per word
+#if GSB_BX_RING
+    if (INT) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        ring[(i + 2 * R) % (2 * R + 1)][k] = e[k];
+        L[k] = ring[i % (2 * R + 1)][k];
+      }
+    } else
+#endif
     unpack_pairs(*reinterpret_cast<const uint2 *>(in + i * BX_PW), L);
     // column sums of columns x-8 .. x+15 as pair words V[0..11]; V[4..7] are this lane's own
     uint32_t V[12], T[4];

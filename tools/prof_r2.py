@@ -22,6 +22,12 @@ if op in ("blur_sobel", "box15", "integral", "resize", "resize_odd", "blur5", "s
         elif op == "integral": ii = api.integral_batch(src)
         elif op == "resize": api.resize_batch(src, 2048, 2048)
         elif op == "resize_odd": api.resize_batch(src, 2560, 1440)
+elif op == "integral_uhd":
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 150          # 150 x 4 strips = 600 CTAs: the 1024-column strip kernel
+    src = torch.randint(0, 256, (n, 2160, 3840), dtype=torch.uint8, device="cuda")
+    ii = torch.empty((n, 2160, 3840), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        api.integral_batch(src, out=ii)
 elif op in ("fast", "orb"):
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     src = api.blur_batch(torch.randint(0, 256, (n, 1080, 1920), dtype=torch.uint8, device="cuda"), 3)
