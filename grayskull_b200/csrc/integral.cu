@@ -188,99 +188,88 @@ k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, uns
 #undef IB_LOAD_ROW
 }
 
-// ---- round 2: k_integral_strips -- no inter-CTA chain on table rows ---------------------------------------------
-// k_integral_bands (below the batch threshold, kept) chains the bands of a frame through a 16 KB table row and a
-// flag: ncu showed 35 % of its stall samples on that spin and 0.69-0.71 of the HBM roofline.  Here a CTA owns a
-// 1024-column STRIP of one frame and walks down ALL its 16-row bands, so the row above a band never leaves the
-// registers (top[8] per thread).  What a strip needs from its left neighbours is one scalar per row: the sum of
-// their band-local column prefixes, SAT(xs-1, y) - SAT(xs-1, y0-1).  Every strip publishes its own row totals
-// of band b as soon as its band-local scan is done (64-bit words carrying a band tag, so no flag / fence pair), and
-// a strip adds up the totals of the strips to its left -- they run in lockstep, nobody waits for a predecessor's
-// OUTPUT, only for its local phase.  Tickets are handed out strip-major, so a strip's left neighbours always hold
-// earlier tickets (they are resident or done: no deadlock).  HBM traffic: 1 B read + 4 B written per pixel.
-#ifndef GSB_IS_BH
-#define GSB_IS_BH 8
-#endif
-constexpr int IS_BH = GSB_IS_BH;              // rows per band of the strip kernel
+// ---- round 2: k_integral_strips -- no inter-CTA chain on table rows, no band-local second pass ------------------
+// k_integral_bands (kept below the batch threshold) chains the bands of a frame through a 16 KB table row and a flag
+// and computes band-local vertical prefixes first (0.69-0.71 of the HBM roofline; ncu: 35 % of the stall samples on
+// the spin, 13.5 lane-instr/px).  Here a CTA owns a 1024-column STRIP of one frame and walks down ALL its rows, RB at
+// a time, with the previous output row in registers:
+//     SAT(x, y) = SAT(x, y-1) + left(y) + sum_{i <= x} src(i, y)
+// per row a thread needs (a) the sum of its 8 pixels -- two IDP.4A against 0x01010101 --, (b) an exclusive scan of
+// those sums over the strip (warp shuffle scan + the warps' totals through shared memory), (c) `left(y)`, the row
+// sums of the strips to its left: every strip publishes its RB row sums as soon as its scan is done (64-bit words
+// carrying a band tag: no flag / fence pair) and a strip adds up the words of its left neighbours -- they run in
+// lockstep, nobody waits for a predecessor's OUTPUT --, and (d) its 8 inclusive in-thread prefixes, ONE IDP.4A each
+// (byte masks 0x01, 0x0101, ...) accumulated straight onto previous row + offset.  ~4.5 instructions per pixel
+// instead of 13.5, ~50-100 registers.  The next RB rows are requested before the current ones are scanned.  Tickets
+// are handed out strip-major, so a strip's left neighbours always hold earlier tickets (resident or done).
 #ifndef GSB_IS_MINB
 #define GSB_IS_MINB 4
 #endif
-constexpr int IS_MINB = GSB_IS_MINB;         // CTAs per SM the register allocation must allow
+constexpr int IS_MINB = GSB_IS_MINB;         // CTAs of 128 threads per SM the register allocation must allow
 
-template <int IS_TPB>
+template <int IS_TPB, int RB>
 __global__ void __launch_bounds__(IS_TPB, IS_MINB * 128 / IS_TPB)
 k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, unsigned w, unsigned h, unsigned n,
                   unsigned strips, unsigned nbands, unsigned *__restrict__ ticket_ctr,
-                  unsigned long long *__restrict__ slots /* [n][strips][nbands][16] : tag << 32 | row total */) {
-  __shared__ uint32_t wtot[IS_BH][IS_TPB / 32];
-  __shared__ uint32_t lsum[IS_BH];
-  __shared__ uint32_t s_off[IS_BH][IS_TPB];   // exclusive horizontal offset of each thread inside its warp, per row
+                  unsigned long long *__restrict__ slots /* [n][strips][nbands][RB] : tag << 32 | row sum of the strip */) {
+  __shared__ uint32_t wtot[RB][IS_TPB / 32];
+  __shared__ uint32_t lsum[RB];
   __shared__ unsigned s_ticket;
+  constexpr int IS_SW = IS_TPB * 8;
+  constexpr uint32_t ONES = 0x01010101u;
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_ticket = atomicAdd(ticket_ctr, 1u);
   __syncthreads();
   const unsigned frame = s_ticket / strips, strip = s_ticket % strips;
-  constexpr int IS_SW = IS_TPB * 8;
   const unsigned x = strip * IS_SW + tid * 8;
   const bool live = x < w;
   const uint8_t *sp = src + (size_t)frame * w * h + x;
   uint32_t *dp = ii + (size_t)frame * w * h + x;
-  unsigned long long *myslots = slots + ((size_t)frame * strips + strip) * nbands * IS_BH;
-  uint32_t top[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long *myslots = slots + ((size_t)frame * strips + strip) * nbands * RB;
+  uint32_t prev[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // the output row above
 
-  // software pipeline: the pixel rows of band b + 1 are requested before band b is scanned and emitted, so that a
-  // CTA always has a band of loads in flight (without it the strips kernel ran at 0.48-0.71 of the HBM roofline)
-  uint2 pxn[IS_BH];
+  uint2 pxn[RB];
 #pragma unroll
-  for (int r = 0; r < IS_BH; r++)
-    pxn[r] = (live && (unsigned)r < h) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)r * w)) : make_uint2(0u, 0u);
+  for (int r = 0; r < RB; r++) {
+    pxn[r] = (live && (unsigned)r < h) ? __ldg(reinterpret_cast<const uint2 *>(sp)) : make_uint2(0u, 0u);
+    sp += w;
+  }
   for (unsigned band = 0; band < nbands; band++) {
-    const unsigned y0 = band * IS_BH, rows = min((unsigned)IS_BH, h - y0);
-    uint2 px[IS_BH];
+    const unsigned y0 = band * RB, rows = min((unsigned)RB, h - y0);
+    uint2 px[RB];
 #pragma unroll
-    for (int r = 0; r < IS_BH; r++) px[r] = pxn[r];
+    for (int r = 0; r < RB; r++) px[r] = pxn[r];
 #pragma unroll
-    for (int r = 0; r < IS_BH; r++) {
-      const unsigned yn = y0 + IS_BH + r;
-      pxn[r] = (live && yn < h) ? __ldg(reinterpret_cast<const uint2 *>(sp + (size_t)yn * w)) : make_uint2(0u, 0u);
+    for (int r = 0; r < RB; r++) {                          // prefetch the next band (sp already points at it)
+      pxn[r] = (live && y0 + RB + r < h) ? __ldg(reinterpret_cast<const uint2 *>(sp)) : make_uint2(0u, 0u);
+      sp += w;
     }
-    // band-local: vertical prefix V (registers), per-row thread totals -> warp scan
-    {
-      uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t off[RB];                                       // exclusive offset of this thread inside its warp, per row
 #pragma unroll
-      for (int r = 0; r < IS_BH; r++) {
+    for (int r = 0; r < RB; r++) {
+      const uint32_t t = __dp4a(px[r].y, ONES, __dp4a(px[r].x, ONES, 0u));
+      uint32_t incl = t;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          acc[c] += (px[r].x >> (8 * c)) & 0xFF;
-          acc[4 + c] += (px[r].y >> (8 * c)) & 0xFF;
-        }
-        const uint32_t t = acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6] + acc[7];
-        uint32_t incl = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-          if (lane >= (unsigned)o) incl += u;
-        }
-        if (lane == 31) wtot[r][warp] = incl;
-        s_off[r][tid] = incl - t;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += u;
       }
+      if (lane == 31) wtot[r][warp] = incl;
+      off[r] = incl - t;
     }
     __syncthreads();
-    // strip totals per row -> publish; sums of the strips to the left -> lsum
-    if (tid < IS_BH) {
+    if (tid < RB) {
       uint32_t tot = 0;
 #pragma unroll
       for (int q = 0; q < IS_TPB / 32; q++) tot += wtot[tid][q];
       if (strip + 1 < strips)
-        *reinterpret_cast<volatile unsigned long long *>(myslots + (size_t)band * IS_BH + tid) =
-            ((unsigned long long)(band + 1) << 32) | tot;
+        *reinterpret_cast<volatile unsigned long long *>(myslots + (size_t)band * RB + tid) = ((unsigned long long)(band + 1) << 32) | tot;
       lsum[tid] = 0;
     }
     __syncthreads();
-    if (strip > 0 && tid < IS_BH * strip && tid < IS_TPB) {
-      // thread (j, r): total of strip j < strip for row r of this band (strips <= 8: at most 112 threads)
-      const unsigned j = tid / IS_BH, r = tid % IS_BH;
-      volatile unsigned long long *sl = slots + (((size_t)frame * strips + j) * nbands + band) * IS_BH + r;
+    for (unsigned i = tid; i < RB * strip; i += IS_TPB) {   // (j, r): row sum r of strip j < strip
+      const unsigned j = i / RB, r = i % RB;
+      volatile unsigned long long *sl = slots + (((size_t)frame * strips + j) * nbands + band) * RB + r;
       unsigned long long v = *sl;
       while ((unsigned)(v >> 32) != band + 1) {
         __nanosleep(20);
@@ -289,32 +278,31 @@ k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, un
       atomicAdd(&lsum[r], (uint32_t)v);
     }
     __syncthreads();
-    // emit the band's rows: SAT = top + left strips + warps to the left + lanes to the left + own prefix
     if (live) {
-      uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      uint32_t o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      uint32_t *q = dp + (size_t)y0 * w;
 #pragma unroll
-      for (int r = 0; r < IS_BH; r++) {
+      for (int r = 0; r < RB; r++) {
         if ((unsigned)r < rows) {
+          uint32_t base = off[r] + lsum[r];
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            v[c] += (px[r].x >> (8 * c)) & 0xFF;
-            v[4 + c] += (px[r].y >> (8 * c)) & 0xFF;
-          }
-          uint32_t run = s_off[r][tid] + lsum[r];
-#pragma unroll
-          for (int q = 0; q < IS_TPB / 32; q++) run += (q < (int)warp) ? wtot[r][q] : 0u;
-#pragma unroll
-          for (int c = 0; c < 8; c++) run += v[c], o[c] = run + top[c];
-          uint4 *q4 = reinterpret_cast<uint4 *>(dp + (size_t)(y0 + r) * w);
-          q4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          q4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          for (int k = 0; k < IS_TPB / 32; k++) base += (k < (int)warp) ? wtot[r][k] : 0u;
+          const uint32_t base2 = __dp4a(px[r].x, ONES, base);
+          prev[0] = __dp4a(px[r].x, 0x00000001u, prev[0] + base);
+          prev[1] = __dp4a(px[r].x, 0x00000101u, prev[1] + base);
+          prev[2] = __dp4a(px[r].x, 0x00010101u, prev[2] + base);
+          prev[3] = prev[3] + base2;
+          prev[4] = __dp4a(px[r].y, 0x00000001u, prev[4] + base2);
+          prev[5] = __dp4a(px[r].y, 0x00000101u, prev[5] + base2);
+          prev[6] = __dp4a(px[r].y, 0x00010101u, prev[6] + base2);
+          prev[7] = __dp4a(px[r].y, ONES, prev[7] + base2);
+          uint4 *q4 = reinterpret_cast<uint4 *>(q);
+          q4[0] = make_uint4(prev[0], prev[1], prev[2], prev[3]);
+          q4[1] = make_uint4(prev[4], prev[5], prev[6], prev[7]);
+          q += w;
         }
       }
-#pragma unroll
-      for (int c = 0; c < 8; c++) top[c] = o[c];          // the band's last row
     }
-    __syncthreads();                                      // wtot / lsum are reused by the next band
+    __syncthreads();                                        // wtot / lsum are reused by the next band
   }
 }
 
@@ -327,27 +315,25 @@ extern "C" int gs_b200_integral_batch(uint32_t *ii, const uint8_t *src, unsigned
   cudaStream_t st = static_cast<cudaStream_t>(s);
   const bool aligned = reinterpret_cast<uintptr_t>(src) % 8 == 0 && reinterpret_cast<uintptr_t>(ii) % 16 == 0;
   {
-    // 1024-column strips (128 threads) when that already fills the machine, else 512-column strips (64 threads)
+    // 1024-column strips of 8 rows per step (128 threads) when that already fills the machine, else 512-column strips
+    // of 16 rows per step (64 threads: twice the CTAs, twice the loads in flight per thread)
     const bool narrow = (unsigned long long)n * ((w + 1023) / 1024) < 592ull && w <= 4096;
-    const unsigned sw_cols = narrow ? 512u : 1024u;
-    const unsigned strips = (w + sw_cols - 1) / sw_cols, nbands = (h + gsb::IS_BH - 1) / gsb::IS_BH;
+    const unsigned sw_cols = narrow ? 512u : 1024u, rb = narrow ? 16u : 8u;
+    const unsigned strips = (w + sw_cols - 1) / sw_cols, nbands = (h + rb - 1) / rb;
     const unsigned long long ctas = (unsigned long long)n * strips;
     const char *env = getenv("GS_B200_INTEGRAL");      // test / A-B hook: "bands" or "strips"
-    // measured (profiles/r02_ab_integral.txt): 256 UHD frames (1024 CTAs) strips 0.714 vs bands 0.713 of the HBM roofline;
-    // 64 frames of 4096^2 (512 narrow CTAs = 7 warps per SM) strips 0.66 vs bands 0.69 -- a strip is w/8 threads per
-    // frame however it is cut, so strips are the default only when the batch alone fills the machine
-    const bool want = env ? env[0] == 's' : (!narrow && ctas >= 592);
-    if (want && !(env && env[0] == 'b') && w % 8 == 0 && strips <= 8 && aligned && !gsb::force_generic() && ctas < 0x7FFFFFFFull) {
-      const size_t slot_bytes = sizeof(unsigned long long) * (size_t)ctas * nbands * gsb::IS_BH;
+    const bool want = env ? env[0] == 's' : ctas >= 148;
+    if (want && !(env && env[0] == 'b') && w % 8 == 0 && strips <= 16 && aligned && !gsb::force_generic() && ctas < 0x7FFFFFFFull) {
+      const size_t slot_bytes = sizeof(unsigned long long) * (size_t)ctas * nbands * rb;
       unsigned char *ws = static_cast<unsigned char *>(gsb::workspace(st, gsb::WS_INTEGRAL, 256 + slot_bytes));
       if (!ws) return (int)cudaErrorMemoryAllocation;
       GSB_CHECK(cudaMemsetAsync(ws, 0, 256 + (strips > 1 ? slot_bytes : 0), st));
       if (narrow)
-        gsb::k_integral_strips<64><<<(unsigned)ctas, 64, 0, st>>>(ii, src, w, h, n, strips, nbands, reinterpret_cast<unsigned *>(ws),
-                                                                 reinterpret_cast<unsigned long long *>(ws + 256));
+        gsb::k_integral_strips<64, 16><<<(unsigned)ctas, 64, 0, st>>>(ii, src, w, h, n, strips, nbands, reinterpret_cast<unsigned *>(ws),
+                                                                     reinterpret_cast<unsigned long long *>(ws + 256));
       else
-        gsb::k_integral_strips<128><<<(unsigned)ctas, 128, 0, st>>>(ii, src, w, h, n, strips, nbands, reinterpret_cast<unsigned *>(ws),
-                                                                   reinterpret_cast<unsigned long long *>(ws + 256));
+        gsb::k_integral_strips<128, 8><<<(unsigned)ctas, 128, 0, st>>>(ii, src, w, h, n, strips, nbands, reinterpret_cast<unsigned *>(ws),
+                                                                      reinterpret_cast<unsigned long long *>(ws + 256));
       GSB_LAUNCHED(1);
       return 0;
     }
