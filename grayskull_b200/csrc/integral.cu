@@ -205,6 +205,9 @@ k_integral_bands(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, uns
 #ifndef GSB_IS_MINB
 #define GSB_IS_MINB 4
 #endif
+#ifndef GSB_IS_CS
+#define GSB_IS_CS 0
+#endif
 constexpr int IS_MINB = GSB_IS_MINB;         // CTAs of 128 threads per SM the register allocation must allow
 
 template <int IS_TPB, int RB>
@@ -295,9 +298,14 @@ k_integral_strips(uint32_t *__restrict__ ii, const uint8_t *__restrict__ src, un
           prev[5] = __dp4a(px[r].y, 0x00000101u, prev[5] + base2);
           prev[6] = __dp4a(px[r].y, 0x00010101u, prev[6] + base2);
           prev[7] = __dp4a(px[r].y, ONES, prev[7] + base2);
+#if GSB_IS_CS
+          st_cs_u4(q, make_uint4(prev[0], prev[1], prev[2], prev[3]));       // streaming: the table is not re-read here
+          st_cs_u4(q + 4, make_uint4(prev[4], prev[5], prev[6], prev[7]));
+#else
           uint4 *q4 = reinterpret_cast<uint4 *>(q);
           q4[0] = make_uint4(prev[0], prev[1], prev[2], prev[3]);
           q4[1] = make_uint4(prev[4], prev[5], prev[6], prev[7]);
+#endif
           q += w;
         }
       }
