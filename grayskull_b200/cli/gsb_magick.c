@@ -10,6 +10,9 @@
  *   blur:R   sobel   erode[:N]   dilate[:N]   adaptive:R:C   threshold:T   threshold:otsu[+K]
  *   filter:sharpen|emboss|box|gaussian   downsample   resize:W:H
  *   keypoints:N:T   (prints the ORB keypoint count per frame; frames pass through unchanged)
+ *   blobs:N         (prints the number of 4-connected components >= 128 per frame; frames pass through unchanged)
+ *   scan:W:H        (the reference's document scanner, nanomagick.c:186-210, per frame on the device: blur 1 ->
+ *                    Otsu + 10 threshold -> blobs -> corners of the largest blob -> perspective warp to W x H)
  * e.g. the reference Makefile's lena chain:  blur:2,threshold:otsu,erode:2,dilate:2
  * Stage semantics are the reference's gs_* functions (same kernels as the drop-in gs_* entry points).
  */
@@ -114,6 +117,63 @@ static void stage(const char *spec, struct batch *cur, struct batch *tmp, size_t
     CK(gs_b200_stream_sync(NULL));
     for (f = 0; f < n; f++) printf("frame %u: %u keypoints\n", f, hc[f]);
     gs_b200_free(kps), gs_b200_free(counts), gs_b200_free(sm), free(hc);
+  } else if (!strcmp(name, "blobs") && nargs == 1) {
+    unsigned nb = (unsigned)atoi(a0), f, *counts, *hc;
+    gs_label *labels;
+    struct gs_blob *blobs;
+    swap = 0;
+    if (nb == 0 || nb > 65534u) DIE("bad blob count in '%s'", spec);
+    labels = (gs_label *)gs_b200_malloc(sizeof(gs_label) * frame_bytes(cur) * n);
+    blobs = (struct gs_blob *)gs_b200_malloc(sizeof(*blobs) * (size_t)nb * n);
+    counts = (unsigned *)gs_b200_malloc(sizeof(unsigned) * n);
+    hc = (unsigned *)malloc(sizeof(unsigned) * n);
+    if (!labels || !blobs || !counts || !hc) DIE("allocation failed");
+    CK(gs_b200_blobs_batch(cur->dev, w, h, n, labels, blobs, counts, nb, NULL));
+    CK(gs_b200_memcpy_d2h(hc, counts, sizeof(unsigned) * n, NULL));
+    CK(gs_b200_stream_sync(NULL));
+    for (f = 0; f < n; f++) printf("frame %u: %u blobs\n", f, hc[f]);
+    gs_b200_free(labels), gs_b200_free(blobs), gs_b200_free(counts), free(hc);
+  } else if (!strcmp(name, "scan") && nargs == 2) {
+    /* reference nanomagick.c:186-210: tmp = blur(img, 1); threshold(tmp, otsu(tmp) + 10); blobs(tmp, 1000); corners of
+     * the largest blob (first one on ties); perspective_correct(out, img, corners) */
+    enum { NB = 1000 };
+    int dw = atoi(a0), dh = atoi(a1);
+    unsigned f, i, *counts, *hc;
+    uint8_t *bin, *th;
+    gs_label *labels;
+    struct gs_blob *blobs, *hb, *pick;
+    struct gs_point *corners;
+    if (dw <= 0 || dh <= 0) DIE("bad size in '%s'", spec);
+    bin = (uint8_t *)gs_b200_malloc(frame_bytes(cur) * n);
+    th = (uint8_t *)gs_b200_malloc(n);
+    labels = (gs_label *)gs_b200_malloc(sizeof(gs_label) * frame_bytes(cur) * n);
+    blobs = (struct gs_blob *)gs_b200_malloc(sizeof(*blobs) * (size_t)NB * n);
+    pick = (struct gs_blob *)gs_b200_malloc(sizeof(*pick) * n);
+    corners = (struct gs_point *)gs_b200_malloc(sizeof(*corners) * 4 * n);
+    counts = (unsigned *)gs_b200_malloc(sizeof(unsigned) * n);
+    hc = (unsigned *)malloc(sizeof(unsigned) * n);
+    hb = (struct gs_blob *)malloc(sizeof(*hb) * (size_t)NB * n);
+    if (!bin || !th || !labels || !blobs || !pick || !corners || !counts || !hc || !hb) DIE("allocation failed");
+    CK(gs_b200_blur_batch(bin, cur->dev, w, h, n, 1, NULL));
+    CK(gs_b200_otsu_threshold_batch(th, NULL, bin, w, h, n, NULL));
+    CK(gs_b200_threshold_each_batch(bin, w, h, n, th, 10, NULL));
+    CK(gs_b200_blobs_batch(bin, w, h, n, labels, blobs, counts, NB, NULL));
+    CK(gs_b200_memcpy_d2h(hc, counts, sizeof(unsigned) * n, NULL));
+    CK(gs_b200_memcpy_d2h(hb, blobs, sizeof(*hb) * (size_t)NB * n, NULL));
+    CK(gs_b200_stream_sync(NULL));
+    for (f = 0; f < n; f++) { /* the selection is a host-side scan of <= 1000 records, like the reference's */
+      unsigned largest = 0;
+      if (hc[f] == 0) memset(&hb[(size_t)f * NB], 0, sizeof(*hb)); /* no blob: corners fall back to the centroid (0, 0) */
+      for (i = 1; i < hc[f]; i++)
+        if (hb[(size_t)f * NB + i].area > hb[(size_t)f * NB + largest].area) largest = i;
+      CK(gs_b200_memcpy_h2d(pick + f, &hb[(size_t)f * NB + largest], sizeof(*pick), NULL));
+      CK(gs_b200_blob_corners(bin + frame_bytes(cur) * f, w, h, labels + frame_bytes(cur) * f, pick + f, corners + 4 * f, NULL));
+    }
+    ensure(tmp, (unsigned)dw, (unsigned)dh, n, cap_tmp);
+    CK(gs_b200_perspective_correct_batch(tmp->dev, (unsigned)dw, (unsigned)dh, cur->dev, w, h, n, corners, 1, NULL));
+    CK(gs_b200_stream_sync(NULL));
+    gs_b200_free(bin), gs_b200_free(th), gs_b200_free(labels), gs_b200_free(blobs), gs_b200_free(pick), gs_b200_free(corners);
+    gs_b200_free(counts), free(hc), free(hb);
   } else {
     DIE("unknown stage or wrong argument count: '%s'", spec);
   }

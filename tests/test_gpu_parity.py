@@ -415,6 +415,40 @@ def test_cli_batch_pipeline(G, O, tmp_path):
         x = x.copy(); O.gso_threshold(L.ptr(x), w, h, t)
         x = o_resize(O, o_down(O, x), 100, 37)
         assert np.array_equal(read(str(tmp_path / ("b_%04d.pgm" % f))), x), f
+    # the reference's document scanner (nanomagick.c:186-210) as one device-resident stage, and the blob counter
+    rng = np.random.default_rng(5)
+    docs = []
+    for f in range(2):
+        doc = np.full((300, 400), 40, np.int16) + rng.integers(-8, 9, (300, 400))
+        yy, xx = np.mgrid[0:300, 0:400]
+        inside = (yy > 40 + xx * 0.05 + 7 * f) & (yy < 250 - xx * 0.04) & (xx > 60 + yy * 0.08) & (xx < 340 - yy * 0.03 - 11 * f)
+        doc[inside] = 210 + rng.integers(-10, 11, int(inside.sum()))
+        docs.append(np.clip(doc, 0, 255).astype(np.uint8))
+    dpaths = []
+    for f, a in enumerate(docs):
+        pth = tmp_path / ("doc%d.pgm" % f)
+        pth.write_bytes(b"P5\n400 300\n255\n" + a.tobytes())
+        dpaths.append(str(pth))
+    r = subprocess.run([exe, "blobs:500,scan:160:200", str(tmp_path / "s_")] + dpaths, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for f, a in enumerate(docs):
+        lab = np.zeros(a.shape, np.uint16); bl = np.zeros(500, L.BLOB_DTYPE)
+        assert ("frame %d: %d blobs" % (f, O.gso_blobs(L.ptr(a), 400, 300, L.ptr(lab), L.ptr(bl), 500))) in r.stdout
+        x = o_blur(O, a, 1)
+        t = (O.gso_otsu_threshold(L.ptr(x), 400, 300) + 10) & 255
+        x = x.copy(); O.gso_threshold(L.ptr(x), 400, 300, t)
+        lab = np.zeros(a.shape, np.uint16); bl = np.zeros(1000, L.BLOB_DTYPE)
+        m = O.gso_blobs(L.ptr(x), 400, 300, L.ptr(lab), L.ptr(bl), 1000)
+        assert m > 0
+        largest = 0
+        for i in range(1, m):
+            if bl["area"][i] > bl["area"][largest]:
+                largest = i
+        c = np.zeros((4, 2), np.uint32)
+        O.gso_blob_corners(L.ptr(x), 400, 300, L.ptr(lab), L.ptr(bl[largest:largest + 1]), L.ptr(c))
+        want = np.empty((200, 160), np.uint8)
+        O.gso_perspective_correct(L.ptr(want), 160, 200, L.ptr(a), 400, 300, L.ptr(c))
+        assert np.array_equal(read(str(tmp_path / ("s_%04d.pgm" % f))), want), f
 
 
 def test_reference_cli_overlay_vs_cpu(tmp_path):

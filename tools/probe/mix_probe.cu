@@ -25,34 +25,42 @@ __global__ void k_copy(uint4 *__restrict__ out, const uint4 *__restrict__ in, si
 __global__ void k_fill(uint4 *__restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = make_uint4(1, 2, 3, 4);
 }
-template <class F> static double best(F f, double bytes) {
+static float time_best(int which, int blocks, int threads, uint32_t *out, const uint8_t *in, size_t npx) {
   cudaEvent_t a, b;
   cudaEventCreate(&a), cudaEventCreate(&b);
   float ms, mn = 1e9f;
   for (int r = 0; r < 12; r++) {
     cudaEventRecord(a);
-    f();
+    if (which == 0) k_expand<<<blocks, threads>>>(out, in, npx / 8, 0);
+    else if (which == 1) k_expand<<<blocks, threads>>>(out, in, npx / 8, 1);
+    else if (which == 2) k_copy<<<blocks, threads>>>((uint4 *)out, (const uint4 *)(out + npx / 2), npx / 8);
+    else k_fill<<<blocks, threads>>>((uint4 *)out, npx / 4);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     cudaEventElapsedTime(&ms, a, b);
     if (r >= 2 && ms < mn) mn = ms;
   }
-  return bytes / (mn * 1e-3) / 1e9;
+  cudaEventDestroy(a), cudaEventDestroy(b);
+  return mn;
 }
 int main() {
-  const size_t npx = (size_t)1 << 31;     // 2 Gi pixels: 2 GiB in, 8 GiB out
-  uint8_t *in;
-  uint32_t *out;
-  cudaMalloc(&in, npx);
-  cudaMalloc(&out, npx * 4);
+  const size_t npx = (size_t)1 << 30;     // 1 Gi pixels: 1 GiB in, 4 GiB out
+  uint8_t *in = nullptr;
+  uint32_t *out = nullptr;
+  if (cudaMalloc(&in, npx) != cudaSuccess || cudaMalloc(&out, npx * 4) != cudaSuccess) {
+    printf("allocation failed\n");
+    return 1;
+  }
   cudaMemset(in, 7, npx);
   const int blocks = 148 * 16;
-  for (int threads : {128, 256, 512}) {
-    printf("threads %d: expand 1:4 plain %.0f GB/s, st.cs %.0f GB/s | copy 1:1 %.0f GB/s | fill %.0f GB/s\n", threads,
-           best([&] { k_expand<<<blocks, threads>>>(out, in, npx / 8, 0); }, 5.0 * npx),
-           best([&] { k_expand<<<blocks, threads>>>(out, in, npx / 8, 1); }, 5.0 * npx),
-           best([&] { k_copy<<<blocks, threads>>>((uint4 *)out, (const uint4 *)(out + npx), npx / 8); }, 4.0 * npx),
-           best([&] { k_fill<<<blocks, threads>>>((uint4 *)out, npx / 4); }, 4.0 * npx));
+  const int tl[3] = {128, 256, 512};
+  for (int t = 0; t < 3; t++) {
+    const int threads = tl[t];
+    const double e0 = 5.0 * npx / (time_best(0, blocks, threads, out, in, npx) * 1e-3) / 1e9;
+    const double e1 = 5.0 * npx / (time_best(1, blocks, threads, out, in, npx) * 1e-3) / 1e9;
+    const double cp = 4.0 * npx / (time_best(2, blocks, threads, out, in, npx) * 1e-3) / 1e9;   // npx/8 uint4 read + written
+    const double fl = 4.0 * npx / (time_best(3, blocks, threads, out, in, npx) * 1e-3) / 1e9;
+    printf("threads %d: expand 1:4 plain %.0f GB/s, st.cs %.0f GB/s | copy 1:1 %.0f GB/s | fill %.0f GB/s\n", threads, e0, e1, cp, fl);
   }
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
