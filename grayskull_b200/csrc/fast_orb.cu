@@ -39,6 +39,30 @@ __device__ const uint32_t c_brief[256] = {
 #include "brief_pattern.inc"
 };
 
+// the same offsets as floats (x1, y1, x2, y2): k_orb_brief converts nothing on the conversion pipe (four I2F per lane and
+// pattern word ran at 16 lanes/clk/SM next to the four float->int truncations).  Filled once per device by k_brief_init.
+__device__ float4 c_brieff[256];
+static const uint32_t h_brief[256] = {
+#include "brief_pattern.inc"
+};
+// once per device, synchronous (cudaMemcpyToSymbol from pageable memory returns after the copy): no stream can see a
+// half-filled table
+static int brief_table_init() {
+  static std::mutex mu;
+  static DeviceOnce once;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!once.needed()) return 0;
+  float4 t[256];
+  for (int i = 0; i < 256; i++) {
+    const uint32_t pk = h_brief[i];
+    t[i] = make_float4((float)(int)(int8_t)(pk & 0xFF), (float)(int)(int8_t)((pk >> 8) & 0xFF),
+                       (float)(int)(int8_t)((pk >> 16) & 0xFF), (float)(int)(int8_t)(pk >> 24));
+  }
+  GSB_CHECK(cudaMemcpyToSymbol(c_brieff, t, sizeof(t)));
+  once.done();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // glibc 2.39 sinf (sysdeps/ieee754/flt-32/s_sinf.c, sincosf.h; double evaluation) and atan2f /
 // atanf (e_atan2f.c, s_atanf.c; float evaluation), restated with explicitly rounded ops.
@@ -665,6 +689,7 @@ k_nms_emit_masks(const uint8_t *__restrict__ score, unsigned sw, unsigned sh, un
   const unsigned f = (unsigned)(gw / rows), row = (unsigned)(gw % rows), y = 3 + row;
   unsigned base = rowoff[gw];
   if (base >= nkps) return;
+  if (row + 1 < rows && rowoff[gw + 1] == base) return;   // no survivor in this row (exclusive offsets: next == own)
   const unsigned *mrow = masks + gw * mw;
   const uint8_t *sm = score + (size_t)f * sw * sh;
   for (unsigned w0 = 0; w0 < mw && base < nkps; w0 += 32) {
@@ -945,9 +970,8 @@ k_orb_brief(const uint8_t *__restrict__ src, unsigned w, unsigned h, KpRec *__re
     const int ox = x - xa;                               // keypoint column inside the patch
 #pragma unroll
     for (int kk = 0; kk < 8; kk++) {
-      const uint32_t pk = __ldg(&c_brief[32 * kk + lane]);
-      const float p0 = (float)(int)(int8_t)(pk & 0xFF), p1 = (float)(int)(int8_t)((pk >> 8) & 0xFF);
-      const float p2 = (float)(int)(int8_t)((pk >> 16) & 0xFF), p3 = (float)(int)(int8_t)(pk >> 24);
+      const float4 pf = __ldg(&c_brieff[32 * kk + lane]);
+      const float p0 = pf.x, p1 = pf.y, p2 = pf.z, p3 = pf.w;
       const int dx1 = __float2int_rz(__fsub_rn(__fmul_rn(p0, cos_a), __fmul_rn(p1, sin_a)));
       const int dy1 = __float2int_rz(__fadd_rn(__fmul_rn(p0, sin_a), __fmul_rn(p1, cos_a)));
       const int dx2 = __float2int_rz(__fsub_rn(__fmul_rn(p2, cos_a), __fmul_rn(p3, sin_a)));
@@ -1159,6 +1183,7 @@ int gs_b200_orb_extract_batch(const uint8_t *src, unsigned w, unsigned h, unsign
   if (gsb::g_trig_mode == 0) gsb::trig_selfcheck_once(st);
   gsb::k_orb_moments<<<(unsigned)blocks, 256, 0, st>>>(src, w, h, kr, counts, nkps, n);
   gsb::k_orb_trig<<<(unsigned)((warps + 255) / 256), 256, 0, st>>>(kr, counts, nkps, n, gsb::g_trig_mode);
+  if (int rcb = gsb::brief_table_init()) return rcb;
   if (w % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0 && !gsb::force_generic())
     gsb::k_orb_brief<true><<<(unsigned)blocks, 256, 0, st>>>(src, w, h, kr, counts, nkps, n);
   else
