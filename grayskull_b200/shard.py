@@ -109,7 +109,8 @@ class ShardedRun:
         if self.rank == src:
             res = pipe.results(0)
             self.gathered = [torch.empty((n_total,) + tuple(res[k].shape[1:]), dtype=res[k].dtype, device=device) for k in keys]
-        self.comm = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        self.cuda = torch.device(device).type == "cuda"
+        self.comm = torch.cuda.Stream(device=device) if self.cuda else None      # CPU / gloo: same schedule, no streams
 
     def bytes_scattered(self):
         """bytes leaving the root (its own shard is a local copy)"""
@@ -129,6 +130,12 @@ class ShardedRun:
 
     # ---- whole shard: scatter, compute, gather back to back on the current stream --------------------------
     def run_serial(self, root_frames):
+        if not self.cuda:
+            scatter_frames(root_frames, self.n_total, (self.h, self.w), torch.uint8, self.device, self.src, self.group, out=self.mine)
+            self.pipe.run(self.mine, 0)
+            res = self.pipe.results(self.m)
+            gather_many([res[k] for k in self.keys], self.n_total, self.src, self.group, out=self.gathered)
+            return None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         scatter_frames(root_frames, self.n_total, (self.h, self.w), torch.uint8, self.device, self.src, self.group, out=self.mine)
@@ -144,16 +151,22 @@ class ShardedRun:
     def run_overlapped(self, root_frames, nchunks):
         """Every rank's shard is cut into `nchunks` equal pieces (the last may be short); piece c of ALL ranks is
         scattered in one NCCL group, so the root's egress stays busy while piece c-1 is being processed, and piece
-        c's results are gathered while piece c+1 is processed."""
-        cur = torch.cuda.current_stream(self.device)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(cur)
-        self.comm.wait_stream(cur)
+        c's results are gathered while piece c+1 is processed.  On a CPU group (gloo tests) the same schedule runs
+        without streams."""
+        import contextlib
+        cuda = self.cuda
+        side = (lambda: torch.cuda.stream(self.comm)) if cuda else contextlib.nullcontext
+        cur = torch.cuda.current_stream(self.device) if cuda else None
+        e0 = e1 = None
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            self.comm.wait_stream(cur)
         per = max((r_hi - r_lo for r_lo, r_hi in (shard_range(self.n_total, r, self.world) for r in range(self.world))))
         csz = (per + nchunks - 1) // nchunks
-        arrived, done = [], []
+        arrived = []
         # scatter pieces (side stream)
-        with torch.cuda.stream(self.comm):
+        with side():
             for c in range(nchunks):
                 ops = []
                 for r in range(self.world):
@@ -169,20 +182,24 @@ class ShardedRun:
                     elif r == self.rank:
                         ops.append(dist.P2POp(dist.irecv, self.mine[pa - a:pb - a], self.src, self.group))
                 _run(ops)
-                e = torch.cuda.Event()
-                e.record(self.comm)
-                arrived.append(e)
+                if cuda:
+                    e = torch.cuda.Event()
+                    e.record(self.comm)
+                    arrived.append(e)
         # compute pieces (current stream), each followed by its gather on the side stream
         res = self.pipe.results(self.m)
         for c in range(nchunks):
             pa, pb = min(c * csz, self.m), min((c + 1) * csz, self.m)
-            cur.wait_event(arrived[c])
+            if cuda:
+                cur.wait_event(arrived[c])
             if pb > pa:
                 self.pipe.run(self.mine[pa:pb], pa)
-            e = torch.cuda.Event()
-            e.record(cur)
-            with torch.cuda.stream(self.comm):
-                self.comm.wait_event(e)
+            if cuda:
+                e = torch.cuda.Event()
+                e.record(cur)
+            with side():
+                if cuda:
+                    self.comm.wait_event(e)
                 ops = []
                 for r in range(self.world):
                     a, b = shard_range(self.n_total, r, self.world)
@@ -198,6 +215,7 @@ class ShardedRun:
                         elif r == self.rank:
                             ops.append(dist.P2POp(dist.isend, res[k][qa - a:qb - a], self.src, self.group))
                 _run(ops)
-        cur.wait_stream(self.comm)
-        e1.record(cur)
+        if cuda:
+            cur.wait_stream(self.comm)
+            e1.record(cur)
         return e0, e1

@@ -370,6 +370,59 @@ dist.barrier(); dist.destroy_process_group(); print("ok", rank)
 '''
 
 
+_WORKER_RUN = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from grayskull_b200.shard import ShardedRun, shard_range
+world = int(sys.argv[4])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=world)
+rank = dist.get_rank()
+
+class FakePipe:      # a per-frame "op" with two result tensors: the schedule and the index arithmetic are what is tested
+    def __init__(self, n, h, w):
+        self.out = torch.zeros((n, h, w), dtype=torch.uint8); self.tag = torch.zeros((n,), dtype=torch.int32)
+    def run(self, frames, lo):
+        m = frames.shape[0]
+        if m == 0:
+            return
+        self.out[lo:lo + m] = 255 - frames
+        self.tag[lo:lo + m] = frames.reshape(m, -1)[:, 0].to(torch.int32) + 1000
+    def results(self, m):
+        return {"out": self.out[:m], "tag": self.tag[:m]}
+
+h, w = 3, 8
+for n in (7, 2, 13):                 # ragged shards, a rank with an empty shard (n=2, world=3), several pieces
+    full = ((torch.arange(n * h * w, dtype=torch.int64) * 7) % 251).to(torch.uint8).reshape(n, h, w)
+    lo, hi = shard_range(n, rank, world)
+    for mode in ("serial", 1, 2, 5):
+        pipe = FakePipe(hi - lo, h, w)
+        run = ShardedRun(pipe, n, h, w, torch.device("cpu"), keys=("out", "tag"))
+        if mode == "serial":
+            run.run_serial(full if rank == 0 else None)
+        else:
+            run.run_overlapped(full if rank == 0 else None, mode)
+        dist.barrier()
+        if rank == 0:
+            assert torch.equal(run.gathered[0], 255 - full), (n, mode)
+            assert torch.equal(run.gathered[1], full.reshape(n, -1)[:, 0].to(torch.int32) + 1000), (n, mode)
+dist.barrier(); dist.destroy_process_group(); print("ok", rank)
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_run_schedule_gloo(tmp_path, world):
+    """ShardedRun (scatter -> per-rank pipeline -> gather; whole shard and in overlapped pieces) on a CPU group:
+    ragged shards, an empty shard, more pieces than frames"""
+    script = tmp_path / "worker_run.py"
+    script.write_text(_WORKER_RUN)
+    port = str(30500 + (os.getpid() + world) % 1000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), str(world)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 def test_scatter_gather_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
