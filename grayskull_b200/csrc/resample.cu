@@ -179,6 +179,95 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
   }
 }
 
+// ---- [r2] k_resize_tiled: source region staged in shared memory ------------------------------------------------
+// The gather kernel above is issue-bound at ~46 instructions per dst pixel (ncu, profiles/r02_ncu_resize.txt): 12 of them
+// are the 64-bit address arithmetic of sixteen byte gathers per thread and row.  Here a CTA first copies the source
+// rectangle its 128 x 64 dst tile can touch into shared memory (coalesced word loads, clamped at the right / bottom
+// image edge so that x1 = min(x0+1, sw-1) and y1 = min(y0+1, sh-1) are plain neighbours in the staged copy), then every
+// tap is an LDS.U8 at a 32-bit offset: 4 address adds + 4 loads per pixel.  Same fp32 evaluation as k_resize.
+// Used when the staged rectangle fits (any ratio up to about 2.8 : 1 per axis, all up-scalings).
+constexpr int RT_MAX_BYTES = 64 * 1024;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_resize_tiled(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src, unsigned sw,
+               unsigned sh, unsigned n, unsigned pitch /* bytes, multiple of 4 */, unsigned max_rows, bool words_ok) {
+  extern __shared__ __align__(16) uint8_t s_tile[];
+  __shared__ unsigned s_y0[8 * RS_ROWS], s_y1[8 * RS_ROWS];
+  __shared__ float s_dy[8 * RS_ROWS];
+  __shared__ unsigned s_reg[4];                      // cxa (aligned-down first column), cya (first row), rows, words
+  const unsigned tid = threadIdx.x;
+  const unsigned tx0 = blockIdx.x * 128, ty0 = blockIdx.y * 8 * RS_ROWS;
+  if (tid < 8 * RS_ROWS) {
+    const unsigned yy = ty0 + tid;
+    unsigned a = 0, b = 0;
+    float fr = 0.0f;
+    if (yy < dh) resize_axis(yy, sh, dh, a, b, fr);
+    s_y0[tid] = a, s_y1[tid] = b, s_dy[tid] = fr;
+  }
+  if (tid == 0) {   // the mapping is monotonic: the tile's first / last pixel bound the rectangle
+    unsigned a0, b0, a1, b1;
+    float f;
+    resize_axis(tx0, sw, dw, a0, b0, f);
+    resize_axis(min(tx0 + 127u, dw - 1), sw, dw, a1, b1, f);
+    const unsigned cxa = a0 & ~3u;
+    s_reg[0] = cxa, s_reg[3] = (b1 - cxa) / 4 + 1;
+    resize_axis(ty0, sh, dh, a0, b0, f);
+    resize_axis(min(ty0 + 8u * RS_ROWS - 1, dh - 1), sh, dh, a1, b1, f);
+    s_reg[1] = a0, s_reg[2] = b1 - a0 + 1;
+  }
+  __syncthreads();
+  const unsigned cxa = s_reg[0], cya = s_reg[1], rrows = min(s_reg[2], max_rows), rwords = min(s_reg[3], pitch / 4);
+  const unsigned x = tx0 + (tid & 31) * 4;
+  const unsigned yl = (tid >> 5) * RS_ROWS, yb = ty0 + yl;
+  unsigned ox0[4], ox1[4];
+  float dx[4], omx[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    unsigned a, b;
+    resize_axis(min(x + j, dw - 1), sw, dw, a, b, dx[j]);
+    omx[j] = __fsub_rn(1.0f, dx[j]);
+    ox0[j] = a - cxa, ox1[j] = b - cxa;
+  }
+  for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
+    const uint8_t *s = src + (size_t)f * sw * sh;
+    uint8_t *d = dst + (size_t)f * dw * dh;
+    __syncthreads();                                       // the previous frame's taps are done
+    for (unsigned i = tid; i < rrows * rwords; i += 256) { // stage: a word per thread and step
+      const unsigned rr = i / rwords, k = i % rwords;
+      const unsigned gy = min(cya + rr, sh - 1), gx = cxa + 4 * k;
+      const uint8_t *row = s + (size_t)gy * sw;
+      uint32_t v;
+      if (words_ok && gx + 3 < sw) {
+        v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+      } else {
+        v = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) v |= (uint32_t)__ldg(row + min(gx + b, sw - 1)) << (8 * b);
+      }
+      *reinterpret_cast<uint32_t *>(s_tile + rr * pitch + 4 * k) = v;
+    }
+    __syncthreads();
+    if (x < dw && yb < dh) {
+      for (unsigned r = 0; r < (unsigned)RS_ROWS && yb + r < dh; r++) {
+        const float dy = s_dy[yl + r], omy = __fsub_rn(1.0f, dy);
+        const uint8_t *r0 = s_tile + (s_y0[yl + r] - cya) * pitch, *r1 = s_tile + (s_y1[yl + r] - cya) * pitch;
+        float p[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          p[j] = bilerp(u8_f(r0[ox0[j]]), u8_f(r0[ox1[j]]), u8_f(r1[ox0[j]]), u8_f(r1[ox1[j]]), omx[j], dx[j], omy, dy);
+        const uint32_t out = prmt(prmt(f_trunc_bits(p[0]), f_trunc_bits(p[1]), 0x0040), prmt(f_trunc_bits(p[2]), f_trunc_bits(p[3]), 0x0040), 0x5410);
+        uint8_t *q = d + (size_t)(yb + r) * dw + x;
+        if (VEC) {
+          *reinterpret_cast<uint32_t *>(q) = out;
+        } else {
+          for (unsigned j = 0; j < 4 && x + j < dw; j++) q[j] = (uint8_t)(out >> (8 * j));
+        }
+      }
+    }
+  }
+}
+
 }  // namespace gsb
 
 extern "C" {
@@ -214,7 +303,33 @@ int gs_b200_resize_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *
   dim3 grid((dw + 127) / 128, (dh + 8 * gsb::RS_ROWS - 1) / (8 * gsb::RS_ROWS), n < 65535u ? n : 65535u);
   GSB_ASSERT(grid.y <= 65535u);
   const bool aligned8 = sw % 8 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0;   // every source row 8-byte aligned
-  if (dw % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0)
+  const bool vec_dst = dw % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % 4 == 0;
+  {
+    // staged-tile kernel: bound the source rectangle of a 128 x 64 dst tile (+3 columns of alignment slack, +2 rows / columns
+    // of neighbours) and use it when it fits the shared-memory budget
+    const double rx = (double)sw / dw, ry = (double)sh / dh;
+    const unsigned cols = (unsigned)(127.0 * rx) + 10, rows = (unsigned)((8.0 * gsb::RS_ROWS - 1) * ry) + 6;   // 2 spare: fp32 vs double
+    const unsigned pitch = (cols + 3) / 4 * 4 + 4;
+    const size_t bytes = (size_t)pitch * rows;
+    const char *env = getenv("GS_B200_RESIZE");          // A/B hook: "gather" forces the round-1 kernel
+    const bool pairs_case = aligned8 && sw == 2 * dw;     // exact 2:1 in x: the 64-bit pair loads of k_resize are already good
+    if (bytes <= (size_t)gsb::RT_MAX_BYTES && !(env && env[0] == 'g') && !pairs_case && !gsb::force_generic()) {
+      static gsb::DeviceOnce once;
+      if (once.needed()) {
+        GSB_CHECK(cudaFuncSetAttribute(gsb::k_resize_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsb::RT_MAX_BYTES));
+        GSB_CHECK(cudaFuncSetAttribute(gsb::k_resize_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsb::RT_MAX_BYTES));
+        once.done();
+      }
+      const bool words_ok = sw % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0;
+      if (vec_dst)
+        gsb::k_resize_tiled<true><<<grid, 256, bytes, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, pitch, rows, words_ok);
+      else
+        gsb::k_resize_tiled<false><<<grid, 256, bytes, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, pitch, rows, words_ok);
+      GSB_LAUNCHED(1);
+      return 0;
+    }
+  }
+  if (vec_dst)
     gsb::k_resize<true><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, aligned8);
   else
     gsb::k_resize<false><<<grid, 256, 0, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, aligned8);

@@ -975,3 +975,17 @@ def test_lbp_tile_configs(G, O, cas, big):
         want = o_detect(O, cas, ii[i], 4000, 1.1, 1.0, 4.0, 2)
         assert got[i].tobytes() == want.tobytes(), (big, i, len(got[i]), len(want))
         assert len(want) > 3
+
+
+def test_resize_full_size_ratios(G, O):
+    """gs_resize at BASELINE frame sizes through the staged-tile kernel (ratios up to ~2.8:1, up-scaling, ragged targets),
+    the 2:1 dispatch to the downsample kernel and the gather kernel (large ratios), whole frames against the oracle"""
+    import torch
+    rng = np.random.default_rng(19)
+    src = rng.integers(0, 256, (2, 2160, 3840)).astype(np.uint8)
+    src[1] = L.natural_like(3840, 2160, 4)
+    d = dev(src)
+    for (dw, dh) in ((2560, 1440), (1920, 1080), (1500, 2000), (4097, 2161), (3837, 797), (960, 2159), (640, 360), (5000, 300)):
+        got = G.resize_batch(d, dw, dh).cpu().numpy()
+        for i in range(2):
+            assert np.array_equal(got[i], o_resize(O, src[i], dw, dh)), (dw, dh, i)
