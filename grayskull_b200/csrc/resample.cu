@@ -233,19 +233,32 @@ k_resize_tiled(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_
     const uint8_t *s = src + (size_t)f * sw * sh;
     uint8_t *d = dst + (size_t)f * dw * dh;
     __syncthreads();                                       // the previous frame's taps are done
-    for (unsigned i = tid; i < rrows * rwords; i += 256) { // stage: a word per thread and step
-      const unsigned rr = i / rwords, k = i % rwords;
-      const unsigned gy = min(cya + rr, sh - 1), gx = cxa + 4 * k;
-      const uint8_t *row = s + (size_t)gy * sw;
-      uint32_t v;
-      if (words_ok && gx + 3 < sw) {
-        v = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
-      } else {
-        v = 0;
+    // stage: a word per thread and step, eight loads in flight per thread before the first store (a rolled
+    // load -> store loop left one load in flight per thread: 1.02 ms instead of 0.37 for the gather kernel)
+    const unsigned total = rrows * rwords;
+    for (unsigned i0 = tid; i0 < total; i0 += 8 * 256) {
+      uint32_t v[8];
+      unsigned so[8];
 #pragma unroll
-        for (int b = 0; b < 4; b++) v |= (uint32_t)__ldg(row + min(gx + b, sw - 1)) << (8 * b);
+      for (int u = 0; u < 8; u++) {
+        const unsigned i = i0 + u * 256;
+        v[u] = 0, so[u] = 0xFFFFFFFFu;
+        if (i < total) {
+          const unsigned rr = i / rwords, k = i - rr * rwords;
+          const unsigned gy = min(cya + rr, sh - 1), gx = cxa + 4 * k;
+          const uint8_t *row = s + (size_t)gy * sw;
+          so[u] = rr * pitch + 4 * k;
+          if (words_ok && gx + 3 < sw) {
+            v[u] = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; b++) v[u] |= (uint32_t)__ldg(row + min(gx + b, sw - 1)) << (8 * b);
+          }
+        }
       }
-      *reinterpret_cast<uint32_t *>(s_tile + rr * pitch + 4 * k) = v;
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (so[u] != 0xFFFFFFFFu) *reinterpret_cast<uint32_t *>(s_tile + so[u]) = v[u];
     }
     __syncthreads();
     if (x < dw && yb < dh) {
