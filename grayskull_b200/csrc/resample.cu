@@ -233,32 +233,35 @@ k_resize_tiled(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_
     const uint8_t *s = src + (size_t)f * sw * sh;
     uint8_t *d = dst + (size_t)f * dw * dh;
     __syncthreads();                                       // the previous frame's taps are done
-    // stage: a word per thread and step, eight loads in flight per thread before the first store (a rolled
-    // load -> store loop left one load in flight per thread: 1.02 ms instead of 0.37 for the gather kernel)
-    const unsigned total = rrows * rwords;
-    for (unsigned i0 = tid; i0 < total; i0 += 8 * 256) {
-      uint32_t v[8];
-      unsigned so[8];
+    // stage: a warp per source row, a lane per word; 4 rows x 2 words = eight loads in flight per lane before the first
+    // store (a rolled load -> store loop with per-word index division cost 60 instructions per staged word)
+    {
+      const unsigned lane = tid & 31, wrp = tid >> 5;
+      for (unsigned rr0 = wrp; rr0 < rrows; rr0 += 32) {
+        for (unsigned k0 = lane; k0 < rwords; k0 += 64) {
+          uint32_t v[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const unsigned i = i0 + u * 256;
-        v[u] = 0, so[u] = 0xFFFFFFFFu;
-        if (i < total) {
-          const unsigned rr = i / rwords, k = i - rr * rwords;
-          const unsigned gy = min(cya + rr, sh - 1), gx = cxa + 4 * k;
-          const uint8_t *row = s + (size_t)gy * sw;
-          so[u] = rr * pitch + 4 * k;
-          if (words_ok && gx + 3 < sw) {
-            v[u] = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
-          } else {
+          for (int u = 0; u < 8; u++) {
+            const unsigned rr = rr0 + 8 * (u >> 1), k = k0 + 32 * (u & 1);
+            v[u] = 0;
+            if (rr < rrows && k < rwords) {
+              const uint8_t *row = s + (size_t)min(cya + rr, sh - 1) * sw;
+              const unsigned gx = cxa + 4 * k;
+              if (words_ok && gx + 3 < sw) {
+                v[u] = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
+              } else {
 #pragma unroll
-            for (int b = 0; b < 4; b++) v[u] |= (uint32_t)__ldg(row + min(gx + b, sw - 1)) << (8 * b);
+                for (int bb = 0; bb < 4; bb++) v[u] |= (uint32_t)__ldg(row + min(gx + bb, sw - 1)) << (8 * bb);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const unsigned rr = rr0 + 8 * (u >> 1), k = k0 + 32 * (u & 1);
+            if (rr < rrows && k < rwords) *reinterpret_cast<uint32_t *>(s_tile + rr * pitch + 4 * k) = v[u];
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < 8; u++)
-        if (so[u] != 0xFFFFFFFFu) *reinterpret_cast<uint32_t *>(s_tile + so[u]) = v[u];
     }
     __syncthreads();
     if (x < dw && yb < dh) {
