@@ -63,9 +63,6 @@ constexpr int RS_ROWS = 8;
 #ifndef GSB_RS_PAIRS
 #define GSB_RS_PAIRS 1
 #endif
-#ifndef GSB_RS_PIPE
-#define GSB_RS_PIPE 0
-#endif
 
 
 __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c11, float omx, float dx, float omy,
@@ -80,10 +77,26 @@ __device__ __forceinline__ float bilerp(float c00, float c01, float c10, float c
 // dst pixel capped round 1's kernel at ~4 pixels/clk/SM): 0x4B0000bb is the float 2^23 + bb, so one PRMT (ALU pipe)
 // and one exact FADD (FMA pipe) give float(bb); adding 2^23 to p in [0, 256) with round-toward-zero leaves
 // trunc(p) in the low byte.
+//
+// [r2] GSB_RS_DENORM: the u8 -> f32 step disappears altogether.  The bit pattern of a byte b read as a float IS the
+// subnormal b * 2^-149, and a power-of-two scaling commutes with round-to-nearest as long as nothing leaves the normal
+// range: rn(b * 2^-149 * (wx * 2^126)) = rn(b * wx) * 2^-23 and rn(that * (wy * 2^23)) = rn(rn(b * wx) * wy), the
+// reference's two products bit for bit (b * wx >= 2^-11 or 0; the weights are pre-scaled once per thread / per row;
+// FMUL takes subnormal inputs at full rate, the library is built without -ftz).  Per tap: load + 2 FMUL.
+#ifndef GSB_RS_DENORM
+#define GSB_RS_DENORM 1
+#endif
+#if GSB_RS_DENORM
+constexpr float RS_WX_SCALE = 0x1p126f, RS_WY_SCALE = 0x1p23f;
+__device__ __forceinline__ float byte_f(uint32_t w, int k) { return __uint_as_float(prmt(w, 0u, 0x4440u | (unsigned)k)); }
+__device__ __forceinline__ float u8_f(unsigned b) { return __uint_as_float(b); }
+#else
+constexpr float RS_WX_SCALE = 1.0f, RS_WY_SCALE = 1.0f;
 __device__ __forceinline__ float byte_f(uint32_t w, int k) {
   return __fsub_rn(__uint_as_float(prmt(w, 0x4B000000u, 0x7540u | (unsigned)k)), 8388608.0f);
 }
 __device__ __forceinline__ float u8_f(unsigned b) { return __fsub_rn(__uint_as_float(b | 0x4B000000u), 8388608.0f); }
+#endif
 __device__ __forceinline__ uint32_t f_trunc_bits(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)); }  // low byte = (uint8_t)p
 
 template <bool VEC>
@@ -92,13 +105,14 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
          unsigned sh, unsigned n, bool src_aligned8) {
   // the y-axis coefficients (an IEEE division each) of the CTA's 64 rows: once per CTA, not once per thread and row
   __shared__ unsigned s_y0[8 * RS_ROWS], s_y1[8 * RS_ROWS];
-  __shared__ float s_dy[8 * RS_ROWS];
+  __shared__ float s_dy[8 * RS_ROWS], s_omy[8 * RS_ROWS];   // pre-scaled y weights
   if (threadIdx.x < 8 * RS_ROWS) {
     const unsigned yy = blockIdx.y * 8 * RS_ROWS + threadIdx.x;
     unsigned a = 0, b = 0;
     float fr = 0.0f;
     if (yy < dh) resize_axis(yy, sh, dh, a, b, fr);
-    s_y0[threadIdx.x] = a, s_y1[threadIdx.x] = b, s_dy[threadIdx.x] = fr;
+    s_y0[threadIdx.x] = a, s_y1[threadIdx.x] = b;
+    s_dy[threadIdx.x] = __fmul_rn(fr, RS_WY_SCALE), s_omy[threadIdx.x] = __fmul_rn(__fsub_rn(1.0f, fr), RS_WY_SCALE);
   }
   __syncthreads();
   const unsigned x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
@@ -110,7 +124,8 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     resize_axis(min(x + j, dw - 1), sw, dw, x0[j], x1[j], dx[j]);
-    omx[j] = __fsub_rn(1.0f, dx[j]);
+    omx[j] = __fmul_rn(__fsub_rn(1.0f, dx[j]), RS_WX_SCALE);
+    dx[j] = __fmul_rn(dx[j], RS_WX_SCALE);
   }
   bool pairs = GSB_RS_PAIRS && VEC && src_aligned8 && x0[0] % 8 == 0 && x + 3 < dw;
 #pragma unroll
@@ -118,40 +133,10 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
   for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
     const uint8_t *s = src + (size_t)f * sw * sh;
     uint8_t *d = dst + (size_t)f * dw * dh;
-#if GSB_RS_PIPE
-    // EXPERIMENT (not measured yet, off by default): the row loop below computes one row's y coefficients (an
-    // IEEE division), then loads, then interpolates -- a serial latency chain per row.  Here all RS_ROWS rows'
-    // coefficients come first, then all 2 x RS_ROWS 64-bit loads are in flight together, then the arithmetic.
-    if (pairs && yb + RS_ROWS <= dh) {
-      float dyv[RS_ROWS];
-      uint2 av[RS_ROWS], bv[RS_ROWS];
-#pragma unroll
-      for (int r = 0; r < RS_ROWS; r++) {
-        unsigned y0, y1;
-        resize_axis(yb + r, sh, dh, y0, y1, dyv[r]);
-        av[r] = __ldg(reinterpret_cast<const uint2 *>(s + (size_t)y0 * sw + x0[0]));
-        bv[r] = __ldg(reinterpret_cast<const uint2 *>(s + (size_t)y1 * sw + x0[0]));
-      }
-#pragma unroll
-      for (int r = 0; r < RS_ROWS; r++) {
-        const uint2 a = av[r], b = bv[r];
-        const float dy = dyv[r], omy = __fsub_rn(1.0f, dy);
-        const float p0 = bilerp(byte_f(a.x, 0), byte_f(a.x, 1), byte_f(b.x, 0), byte_f(b.x, 1), omx[0], dx[0], omy, dy);
-        const float p1 = bilerp(byte_f(a.x, 2), byte_f(a.x, 3), byte_f(b.x, 2), byte_f(b.x, 3), omx[1], dx[1], omy, dy);
-        const float p2 = bilerp(byte_f(a.y, 0), byte_f(a.y, 1), byte_f(b.y, 0), byte_f(b.y, 1), omx[2], dx[2], omy, dy);
-        const float p3 = bilerp(byte_f(a.y, 2), byte_f(a.y, 3), byte_f(b.y, 2), byte_f(b.y, 3), omx[3], dx[3], omy, dy);
-        *reinterpret_cast<uint32_t *>(d + (size_t)(yb + r) * dw + x) =
-            (__float2uint_rz(p0) & 0xFFu) | ((__float2uint_rz(p1) & 0xFFu) << 8) | ((__float2uint_rz(p2) & 0xFFu) << 16) |
-            ((__float2uint_rz(p3) & 0xFFu) << 24);
-      }
-      continue;
-    }
-#endif
     for (unsigned r = 0; r < (unsigned)RS_ROWS && yb + r < dh; r++) {
       const unsigned y = yb + r;
       const unsigned y0 = s_y0[yl + r], y1 = s_y1[yl + r];
-      const float dy = s_dy[yl + r];
-      const float omy = __fsub_rn(1.0f, dy);
+      const float omy = s_omy[yl + r], dy = s_dy[yl + r];
       const uint8_t *r0 = s + (size_t)y0 * sw, *r1 = s + (size_t)y1 * sw;
       uint32_t out = 0;
       if (pairs) {
@@ -179,99 +164,86 @@ k_resize(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__r
   }
 }
 
-// ---- [r2] k_resize_tiled: source region staged in shared memory ------------------------------------------------
-// The gather kernel above is issue-bound at ~46 instructions per dst pixel (ncu, profiles/r02_ncu_resize.txt): 12 of them
-// are the 64-bit address arithmetic of sixteen byte gathers per thread and row.  Here a CTA first copies the source
-// rectangle its 128 x 64 dst tile can touch into shared memory (coalesced word loads, clamped at the right / bottom
-// image edge so that x1 = min(x0+1, sw-1) and y1 = min(y0+1, sh-1) are plain neighbours in the staged copy), then every
-// tap is an LDS.U8 at a 32-bit offset: 4 address adds + 4 loads per pixel.  Same fp32 evaluation as k_resize.
-// Used when the staged rectangle fits (any ratio up to about 2.8 : 1 per axis, all up-scalings).
+// ---- [r2] k_resize_tiled: source rectangle staged in shared memory by TMA ---------------------------------------
+// The gather kernel above is issue-bound at ~46 instructions per dst pixel (ncu, profiles/r02_ab_resize.txt): 12 of them
+// are the 64-bit address arithmetic of sixteen byte gathers per thread and row.  Here ONE bulk tensor copy brings the
+// source rectangle a 128 x 64 dst tile can touch into shared memory, then every tap is an LDS.U8 at a 32-bit offset:
+// 4 address adds + 4 loads per pixel.  (Staging with ordinary loads was measured first: the index arithmetic per
+// staged word cost more than the gathers it replaced -- 0.20-0.27 of the roofline against 0.54.)  Same fp32 evaluation
+// as k_resize.  Used when the rectangle fits (ratios up to about 2.8 : 1 per axis, all up-scalings) and TMA applies.
 constexpr int RT_MAX_BYTES = 64 * 1024;
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-k_resize_tiled(uint8_t *__restrict__ dst, unsigned dw, unsigned dh, const uint8_t *__restrict__ src, unsigned sw,
-               unsigned sh, unsigned n, unsigned pitch /* bytes, multiple of 4 */, unsigned max_rows, bool words_ok) {
-  extern __shared__ __align__(16) uint8_t s_tile[];
-  __shared__ unsigned s_y0[8 * RS_ROWS], s_y1[8 * RS_ROWS];
-  __shared__ float s_dy[8 * RS_ROWS];
-  __shared__ unsigned s_reg[4];                      // cxa (aligned-down first column), cya (first row), rows, words
+k_resize_tiled(const __grid_constant__ CUtensorMap tmap, uint8_t *__restrict__ dst, unsigned dw, unsigned dh, unsigned sw,
+               unsigned sh, unsigned n, unsigned pitch /* bytes, multiple of 16 = the TMA box width */, unsigned max_rows) {
+  extern __shared__ __align__(128) uint8_t s_tile[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ unsigned s_roff[8 * RS_ROWS];           // byte offset of source row y0 in the staged rectangle
+  __shared__ float s_dy[8 * RS_ROWS], s_omy[8 * RS_ROWS];   // pre-scaled y weights
+  __shared__ unsigned s_reg[2];                      // cxa (first staged column, 16-aligned), cya (first staged row)
   const unsigned tid = threadIdx.x;
   const unsigned tx0 = blockIdx.x * 128, ty0 = blockIdx.y * 8 * RS_ROWS;
-  if (tid < 8 * RS_ROWS) {
-    const unsigned yy = ty0 + tid;
-    unsigned a = 0, b = 0;
-    float fr = 0.0f;
-    if (yy < dh) resize_axis(yy, sh, dh, a, b, fr);
-    s_y0[tid] = a, s_y1[tid] = b, s_dy[tid] = fr;
-  }
   if (tid == 0) {   // the mapping is monotonic: the tile's first / last pixel bound the rectangle
     unsigned a0, b0, a1, b1;
     float f;
     resize_axis(tx0, sw, dw, a0, b0, f);
     resize_axis(min(tx0 + 127u, dw - 1), sw, dw, a1, b1, f);
-    const unsigned cxa = a0 & ~3u;
-    s_reg[0] = cxa, s_reg[3] = (b1 - cxa) / 4 + 1;
+    const unsigned cxa = a0 & ~15u;                  // the inner TMA coordinate must be a multiple of 16 bytes
+    const unsigned cols = a1 + 2 - cxa;              // taps x0 and x0 + 1
     resize_axis(ty0, sh, dh, a0, b0, f);
     resize_axis(min(ty0 + 8u * RS_ROWS - 1, dh - 1), sh, dh, a1, b1, f);
-    s_reg[1] = a0, s_reg[2] = b1 - a0 + 1;
+    s_reg[0] = cxa, s_reg[1] = a0;
+    if (cols > pitch || a1 + 2 - a0 > max_rows) __trap();   // the host's bound covers the tile (with spare); never silently wrong
+    mbar_init(&bar, 1);
+    mbar_fence_init();
   }
   __syncthreads();
-  const unsigned cxa = s_reg[0], cya = s_reg[1], rrows = min(s_reg[2], max_rows), rwords = min(s_reg[3], pitch / 4);
+  const unsigned cxa = s_reg[0], cya = s_reg[1];
+  if (tid < 8 * RS_ROWS) {
+    const unsigned yy = ty0 + tid;
+    unsigned a = cya, b = 0;
+    float fr = 0.0f;
+    if (yy < dh) resize_axis(yy, sh, dh, a, b, fr);
+    s_roff[tid] = (a - cya) * pitch;
+    s_dy[tid] = __fmul_rn(fr, RS_WY_SCALE), s_omy[tid] = __fmul_rn(__fsub_rn(1.0f, fr), RS_WY_SCALE);
+  }
   const unsigned x = tx0 + (tid & 31) * 4;
   const unsigned yl = (tid >> 5) * RS_ROWS, yb = ty0 + yl;
-  unsigned ox0[4], ox1[4];
+  // The second tap of each axis is read at x0 + 1 / y0 + 1 WITHOUT the reference's clamp: x0 == sw - 1 only when the
+  // clamped coordinate is exactly sw - 1, i.e. dx == 0, and then whatever (finite) byte sits at x0 + 1 is multiplied
+  // by zero; same for y.  (TMA zero-fills outside the image and the rectangle has the spare column / row.)
+  unsigned ox0[4];
   float dx[4], omx[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     unsigned a, b;
     resize_axis(min(x + j, dw - 1), sw, dw, a, b, dx[j]);
-    omx[j] = __fsub_rn(1.0f, dx[j]);
-    ox0[j] = a - cxa, ox1[j] = b - cxa;
+    omx[j] = __fmul_rn(__fsub_rn(1.0f, dx[j]), RS_WX_SCALE);
+    dx[j] = __fmul_rn(dx[j], RS_WX_SCALE);
+    ox0[j] = a - cxa;
   }
+  unsigned phase = 0;
   for (unsigned f = blockIdx.z; f < n; f += gridDim.z) {
-    const uint8_t *s = src + (size_t)f * sw * sh;
     uint8_t *d = dst + (size_t)f * dw * dh;
-    __syncthreads();                                       // the previous frame's taps are done
-    // stage: a warp per source row, a lane per word; 4 rows x 2 words = eight loads in flight per lane before the first
-    // store (a rolled load -> store loop with per-word index division cost 60 instructions per staged word)
-    {
-      const unsigned lane = tid & 31, wrp = tid >> 5;
-      for (unsigned rr0 = wrp; rr0 < rrows; rr0 += 32) {
-        for (unsigned k0 = lane; k0 < rwords; k0 += 64) {
-          uint32_t v[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const unsigned rr = rr0 + 8 * (u >> 1), k = k0 + 32 * (u & 1);
-            v[u] = 0;
-            if (rr < rrows && k < rwords) {
-              const uint8_t *row = s + (size_t)min(cya + rr, sh - 1) * sw;
-              const unsigned gx = cxa + 4 * k;
-              if (words_ok && gx + 3 < sw) {
-                v[u] = __ldg(reinterpret_cast<const uint32_t *>(row + gx));
-              } else {
-#pragma unroll
-                for (int bb = 0; bb < 4; bb++) v[u] |= (uint32_t)__ldg(row + min(gx + bb, sw - 1)) << (8 * bb);
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const unsigned rr = rr0 + 8 * (u >> 1), k = k0 + 32 * (u & 1);
-            if (rr < rrows && k < rwords) *reinterpret_cast<uint32_t *>(s_tile + rr * pitch + 4 * k) = v[u];
-          }
-        }
-      }
+    __syncthreads();                                 // the tables are written / the previous frame's taps are done
+    // stage the source rectangle with ONE bulk tensor copy: no instructions per staged byte
+    if (tid == 0) {
+      mbar_expect_tx(&bar, pitch * max_rows);
+      tma_load_3d(s_tile, &tmap, (int)(cxa / 4), (int)cya, (int)f, &bar);
     }
-    __syncthreads();
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
     if (x < dw && yb < dh) {
       for (unsigned r = 0; r < (unsigned)RS_ROWS && yb + r < dh; r++) {
-        const float dy = s_dy[yl + r], omy = __fsub_rn(1.0f, dy);
-        const uint8_t *r0 = s_tile + (s_y0[yl + r] - cya) * pitch, *r1 = s_tile + (s_y1[yl + r] - cya) * pitch;
+        const float omy = s_omy[yl + r], dy = s_dy[yl + r];
+        const uint8_t *t0 = s_tile + s_roff[yl + r];
         float p[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          p[j] = bilerp(u8_f(r0[ox0[j]]), u8_f(r0[ox1[j]]), u8_f(r1[ox0[j]]), u8_f(r1[ox1[j]]), omx[j], dx[j], omy, dy);
+        for (int j = 0; j < 4; j++) {
+          const uint8_t *a = t0 + ox0[j], *b = a + pitch;
+          p[j] = bilerp(u8_f(a[0]), u8_f(a[1]), u8_f(b[0]), u8_f(b[1]), omx[j], dx[j], omy, dy);
+        }
         const uint32_t out = prmt(prmt(f_trunc_bits(p[0]), f_trunc_bits(p[1]), 0x0040), prmt(f_trunc_bits(p[2]), f_trunc_bits(p[3]), 0x0040), 0x5410);
         uint8_t *q = d + (size_t)(yb + r) * dw + x;
         if (VEC) {
@@ -324,23 +296,24 @@ int gs_b200_resize_batch(uint8_t *dst, unsigned dw, unsigned dh, const uint8_t *
     // staged-tile kernel: bound the source rectangle of a 128 x 64 dst tile (+3 columns of alignment slack, +2 rows / columns
     // of neighbours) and use it when it fits the shared-memory budget
     const double rx = (double)sw / dw, ry = (double)sh / dh;
-    const unsigned cols = (unsigned)(127.0 * rx) + 10, rows = (unsigned)((8.0 * gsb::RS_ROWS - 1) * ry) + 6;   // 2 spare: fp32 vs double
-    const unsigned pitch = (cols + 3) / 4 * 4 + 4;
+    const unsigned cols = (unsigned)(127.0 * rx) + 22, rows = (unsigned)((8.0 * gsb::RS_ROWS - 1) * ry) + 6;   // spare: fp32 vs double, 16-byte alignment
+    const unsigned pitch = (cols + 15) / 16 * 16;
     const size_t bytes = (size_t)pitch * rows;
     const char *env = getenv("GS_B200_RESIZE");          // A/B hook: "gather" forces the round-1 kernel
     const bool pairs_case = aligned8 && sw == 2 * dw;     // exact 2:1 in x: the 64-bit pair loads of k_resize are already good
-    if (bytes <= (size_t)gsb::RT_MAX_BYTES && !(env && env[0] == 'g') && !pairs_case && !gsb::force_generic()) {
+    CUtensorMap tm;
+    if (bytes <= (size_t)gsb::RT_MAX_BYTES && pitch <= 1024 && rows <= 256 && !(env && env[0] == 'g') && !pairs_case &&
+        gsb::tma_ok(src, sw) && n <= 65535u && gsb::make_tmap_u8frames(&tm, src, sw, sh, n, pitch / 4, rows)) {
       static gsb::DeviceOnce once;
       if (once.needed()) {
         GSB_CHECK(cudaFuncSetAttribute(gsb::k_resize_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsb::RT_MAX_BYTES));
         GSB_CHECK(cudaFuncSetAttribute(gsb::k_resize_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsb::RT_MAX_BYTES));
         once.done();
       }
-      const bool words_ok = sw % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 4 == 0;
       if (vec_dst)
-        gsb::k_resize_tiled<true><<<grid, 256, bytes, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, pitch, rows, words_ok);
+        gsb::k_resize_tiled<true><<<grid, 256, bytes, static_cast<cudaStream_t>(s)>>>(tm, dst, dw, dh, sw, sh, n, pitch, rows);
       else
-        gsb::k_resize_tiled<false><<<grid, 256, bytes, static_cast<cudaStream_t>(s)>>>(dst, dw, dh, src, sw, sh, n, pitch, rows, words_ok);
+        gsb::k_resize_tiled<false><<<grid, 256, bytes, static_cast<cudaStream_t>(s)>>>(tm, dst, dw, dh, sw, sh, n, pitch, rows);
       GSB_LAUNCHED(1);
       return 0;
     }
