@@ -591,6 +591,307 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
   }
 }
 
+// ---- medium / wide radii, aligned frames: k_box_mid (round 2, second form) ---------------------
+// k_box_wide pays ~37 lane-instructions per pixel: a 256-column prefix scan per row (shuffles + selects) and
+// two scattered LDS per pixel.  This form keeps the same warp-autonomous 256-column segments and the same
+// rolling u16x2 column sums, but turns the horizontal pass into a ROLLING sum too, by transposing through
+// shared memory: a warp alternates between
+//   V-phase : 32 rows; lanes = 8 columns each.  The column sums of a row (256 u16) go to the warp's private
+//             C tile [32 rows][4 u16 pad + 256 u16], pitch 130 words;
+//   H-phase : lanes = ROWS.  Lane j walks row j from left to right with the window sum in one register:
+//             W(c) = W(c-1) + C[c+r] - C[c-r-1], each term one IDP.2A (dp2a reads either 16-bit half of a
+//             pair word through its byte multiplier: 0x0001 / 0x0100 add, 0x00FF / 0xFF00 subtract), the C
+//             values come as 64-bit groups of four (pitch = 2 mod 32 words: conflict-free with lanes on rows);
+//             r mod 4 fixes where the entering / leaving elements sit inside their groups, hence the template
+//             parameter.  Quotients as in k_box_wide.  The 8 output bytes of an iteration overwrite the head
+//             of the lane's own C row (already consumed: byte 16+8t <= 8*(gl0+2t+3));
+//   copy-out: lanes = columns again; rows leave as coalesced 64-bit stores (gs_adaptive_threshold compares
+//             with the centre pixels here, on 16-bit lane pairs).
+// ~10 lane-instructions per pixel instead of ~37; global loads are prefetched 4..8 rows ahead and the
+// batch for the next chunk is in flight during the H-phase.
+#ifndef GSB_BM_PF
+#define GSB_BM_PF 0                         // L2 prefetch of the entering rows a chunk ahead: +3 % time saved, +3.6 % instructions: a wash
+#endif
+constexpr int BM_PITCH = 130;                       // words per C row
+constexpr int BM_WARP_WORDS = 32 * BM_PITCH + 8;    // + the look-ahead groups of the last row
+constexpr int BM_SMEM = BM_WARP_WORDS * 4;         // one warp per CTA: 16.3 KB, 13 CTAs per SM
+
+__device__ const uint2 bm_zero8 = {0u, 0u};
+
+// low bytes of four words -> one word, on the ALU pipe (the H-phase keeps the FMA pipe busy with IDP / FFMA)
+__device__ __forceinline__ uint32_t pack4_alu(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+  return prmt(prmt(q0, q1, 0x0040), prmt(q2, q3, 0x0040), 0x5410);
+}
+
+template <bool SUB>
+__device__ __forceinline__ uint32_t dp2a_half(uint32_t acc, uint32_t word, int half) {
+  uint32_t d;
+  if (!SUB) {
+    if (half) asm("dp2a.lo.u32.u32 %0, %1, 0x0100, %2;" : "=r"(d) : "r"(word), "r"(acc));
+    else asm("dp2a.lo.u32.u32 %0, %1, 0x0001, %2;" : "=r"(d) : "r"(word), "r"(acc));
+  } else {
+    if (half) asm("dp2a.lo.u32.s32 %0, %1, 0xFF00, %2;" : "=r"(d) : "r"(word), "r"(acc));
+    else asm("dp2a.lo.u32.s32 %0, %1, 0x00FF, %2;" : "=r"(d) : "r"(word), "r"(acc));
+  }
+  return d;
+}
+// bytes (b0..b7) of two words -> pair words (b0,b2) (b1,b3) (b4,b6) (b5,b7): half of the unpacking is a plain AND
+// (full-rate LOP3; PRMT issues at half rate, tools/probe/pipe_probe.cu).  The H-phase addresses single halves, so the
+// order of the columns inside a group of four is free: element e of a group sits in word e & 1, half e >> 1.
+__device__ __forceinline__ void unpack_pairs_alt(uint2 v, uint32_t (&p)[4]) {
+  p[0] = v.x & 0x00FF00FFu, p[1] = prmt(v.x, 0, 0x4341);
+  p[2] = v.y & 0x00FF00FFu, p[3] = prmt(v.y, 0, 0x4341);
+}
+// element idx (0..7) of the two groups of four u16 (a, b)
+template <bool SUB>
+__device__ __forceinline__ uint32_t dp2a_elem(uint32_t acc, uint2 a, uint2 b, int idx) {
+  const uint2 g = idx < 4 ? a : b;
+  return dp2a_half<SUB>(acc, (idx & 1) ? g.y : g.x, (idx >> 1) & 1);
+}
+
+template <int RM, bool ADAPTIVE>
+__global__ void __launch_bounds__(32)
+k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int h, int r, int R8, int BH,
+          int strips, int cparam, float minv, int fast_ok, unsigned mulhi) {
+  // one warp per CTA: the warps never synchronise with each other, and a 4-warp CTA held its 66 KB until its slowest
+  // warp had finished (7 of 12 warp slots occupied on average in the first capture)
+  extern __shared__ __align__(16) uint32_t bm_smem[];
+  constexpr int LM = (3 - RM) & 3;
+  const int lane = threadIdx.x;
+  const int wid = (int)blockIdx.x;                              // warps are dealt over (band, strip)
+  const int strip = wid % strips, band = wid / strips;
+  uint32_t *cs = bm_smem;
+  uint32_t *rw = cs + lane * BM_PITCH;                          // H-phase: this lane's row
+  const int outw = 256 - 2 * R8;
+  const int xs = strip * outw - R8;                             // image column of segment column 0 (multiple of 8)
+  const int x0 = xs + 8 * lane;
+  const int yb = band * BH, ye = min(h, yb + BH);
+  const uint8_t *frame = src + (size_t)blockIdx.z * w * h;
+  uint8_t *out = dst + (size_t)blockIdx.z * w * h;
+  const bool lane_in = x0 >= 0 && x0 < w;                       // w % 8 == 0
+  const bool out_lane = 8 * lane >= R8 && 8 * lane + 8 <= 256 - R8 && x0 < w;
+  const int FULL = 2 * r + 1;
+
+  rw[0] = 0u, rw[1] = 0u;                                       // C[-4..-1] = 0: what "leaves" before column 0 entered
+  if (lane == 0) cs[32 * BM_PITCH] = 0u, cs[32 * BM_PITCH + 1] = 0u;
+
+  // rows of this lane's 8 columns; lanes left / right of the image read a zero word with stride 0, rows above / below
+  // the image are a warp-uniform test
+  const unsigned wl = lane_in ? (unsigned)w : 0u;
+  const uint8_t *col = lane_in ? frame + x0 : reinterpret_cast<const uint8_t *>(&bm_zero8);
+  auto ld_row = [&](int y) -> uint2 {
+    if ((unsigned)y >= (unsigned)h) return make_uint2(0u, 0u);
+    return __ldg(reinterpret_cast<const uint2 *>(col + (size_t)(unsigned)y * wl));
+  };
+  auto ld_batch = [&](uint2 (&v)[4], int y, auto guard_tag) {   // rows y .. y+3
+    if (!decltype(guard_tag)::value || (y >= 0 && y + 3 < h)) {
+      const uint8_t *p = col + (size_t)(unsigned)y * wl;
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = __ldg(reinterpret_cast<const uint2 *>(p + (size_t)k * wl));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = ld_row(y + k);
+    }
+  };
+  // the rows that enter / leave the window, in batches of four row steps; a ring of four batches keeps the loads
+  // three batches (12 rows) ahead of their use, also across the H-phase
+  uint2 en[4][4], lv[4][4];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    ld_batch(en[i], yb + 4 * i + r + 1, std::true_type{});
+    ld_batch(lv[i], yb + 4 * i - r, std::true_type{});
+  }
+  uint32_t S[4] = {0, 0, 0, 0};                                 // column sums over rows [y - r, y + r], y = yb
+  for (int i0 = -r; i0 <= r; i0 += 16) {                        // 16 loads in flight (one at a time: 2r+1 latencies per band)
+    uint2 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = i0 + k <= r ? ld_row(yb + i0 + k) : make_uint2(0u, 0u);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      uint32_t e[4];
+      unpack_pairs_alt(v[k], e);
+#pragma unroll
+      for (int q = 0; q < 4; q++) S[q] += e[q];
+    }
+  }
+
+  const int cc = max(-256, min(256, cparam));
+  const uint32_t kc = (uint32_t)(cc + 0x7FFF) * 0x10001u;
+  const int ge0 = (R8 + r + 4) >> 2, gl0 = (R8 - r + 3) >> 2;   // first entering / leaving group of a row
+  const int iters = outw >> 3;
+
+  for (int yc = yb; yc < ye; yc += 32) {
+    // ---- V-phase: C rows of image rows yc .. yc+31
+    __syncwarp();                                               // the previous chunk's copy-out is done
+    auto v_phase = [&](auto guard_tag) {
+      uint32_t *crow = cs + 2 + 4 * lane;
+#pragma unroll 1
+      for (int bb = 0; bb < 2; bb++) {
+#pragma unroll
+        for (int qb = 0; qb < 4; qb++) {
+          const int yn = yc + 16 * bb + 4 * qb + 12;            // first row step of the batch three ahead
+          ld_batch(en[(qb + 3) & 3], yn + r + 1, guard_tag);
+          ld_batch(lv[(qb + 3) & 3], yn - r, guard_tag);
+#if GSB_BM_PF
+          if (!decltype(guard_tag)::value) {                    // L2 prefetch of the entering rows one chunk further down
+            const uint8_t *pp = col + (size_t)(unsigned)(yn + r + 1) * wl;
+#pragma unroll
+            for (int k = 0; k < 4; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + (size_t)(k + 32) * wl));
+          }
+#endif
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            *reinterpret_cast<uint2 *>(crow) = make_uint2(S[0], S[1]);
+            *reinterpret_cast<uint2 *>(crow + 2) = make_uint2(S[2], S[3]);
+            crow += BM_PITCH;
+            uint32_t e[4], l[4];
+            unpack_pairs_alt(en[qb][k], e);
+            unpack_pairs_alt(lv[qb][k], l);
+#pragma unroll
+            for (int q = 0; q < 4; q++) S[q] = S[q] + e[q] - l[q];
+          }
+        }
+      }
+    };
+    // every row this chunk loads or prefetches (yc + 12 - r .. yc + 44 + r + 32) is inside the image
+    if (yc + 12 - r >= 0 && yc + 76 + r < h) v_phase(std::false_type{});
+    else v_phase(std::true_type{});
+    __syncwarp();
+    // ---- H-phase: lane = row
+    const int y = yc + lane;
+    if (y < ye) {
+      const uint2 *grp = reinterpret_cast<const uint2 *>(rw);
+      uint2 L0 = grp[gl0], E0 = grp[ge0];
+      uint32_t W = 0;
+#pragma unroll
+      for (int k = LM; k < 4; k++) W = dp2a_elem<false>(W, L0, L0, k);
+      for (int g = gl0 + 1; g < ge0; g++) {
+        const uint2 t = grp[g];
+        asm("dp2a.lo.u32.u32 %0, %1, 0x0101, %0;" : "+r"(W) : "r"(t.x));
+        asm("dp2a.lo.u32.u32 %0, %1, 0x0101, %0;" : "+r"(W) : "r"(t.y));
+      }
+#pragma unroll
+      for (int k = 0; k < RM; k++) W = dp2a_elem<false>(W, E0, E0, k);
+      const int ch = min(y + r, h - 1) - max(y - r, 0) + 1;
+      const bool row_fast = fast_ok && ch == FULL;
+      const uint2 *pe = grp + ge0 + 1, *pl = grp + gl0 + 1;
+      uint2 *po = reinterpret_cast<uint2 *>(rw + 2);
+      const int xo = xs + R8;                                   // image column of this row's first output
+      // eight outputs per step.  MODE 0: clipped windows (per-pixel count); 1: unclipped, magic multiplier on the FMA
+      // pipe; 2: unclipped, 32-bit multiply-high (r <= 31).  The window sums of a group of four are W + D_k with the
+      // D_k chained from zero: the chains of different groups are independent (the single chain W(c) = W(c-1) + .. - ..
+      // left a warp waiting 4 cycles on every IDP), only one add per group is serial.  The groups of the NEXT step are
+      // loaded before this step's arithmetic (the compiler cannot hoist them over the store of the outputs, which
+      // aliases the row as far as it can tell; they lie beyond byte 16 + 8t, see the header).
+      uint2 En[2] = {pe[0], pe[1]}, Ln[2] = {pl[0], pl[1]};
+      auto step8 = [&](int t, auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        const uint2 Ec[2] = {En[0], En[1]}, Lc[2] = {Ln[0], Ln[1]};
+        En[0] = pe[2 * t + 2], En[1] = pe[2 * t + 3], Ln[0] = pl[2 * t + 2], Ln[1] = pl[2 * t + 3];
+        uint32_t ow[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint2 E1 = Ec[s], L1 = Lc[s];
+          uint32_t Wk[4], q[4], D = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            D = dp2a_elem<false>(D, E0, E1, RM + k);
+            D = dp2a_elem<true>(D, L0, L1, LM + k);
+            Wk[k] = W + D;
+          }
+          W = Wk[3];
+          E0 = E1, L0 = L1;
+          if (MODE == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = __umulhi(Wk[k], mulhi);
+          } else if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) q[k] = __float_as_uint(__fmaf_rd((float)Wk[k], minv, 8388608.0f));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              // floor(W / count), count = in-image columns x rows < 2^16, W <= 255 * count: the approximate quotient
+              // (MUFU.RCP, |error| < 1e-3) truncates to the true floor or one off; the remainder decides
+              const int x = xo + 8 * t + 4 * s + k;
+              const int cnt = max(min(x + r, w - 1) - max(x - r, 0) + 1, 1) * ch;   // columns outside the image are never stored
+              uint32_t q0 = (uint32_t)__fdividef((float)Wk[k], (float)cnt);
+              const int rem = (int)Wk[k] - (int)q0 * cnt;
+              q0 += rem >= cnt ? 1u : 0u;
+              q0 -= rem < 0 ? 1u : 0u;
+              q[k] = q0 & 0xFFu;
+            }
+          }
+          ow[s] = pack4_alu(q[0], q[1], q[2], q[3]);
+        }
+        po[t] = make_uint2(ow[0], ow[1]);
+      };
+      // steps that reach into the image: [0, t_img); of those, [t_lo, t_hi) are fast: xo + 8t - r >= 0 and
+      // xo + 8t + 7 + r <= w - 1
+      const int t_img = min(iters, (w - xo + 7) >> 3);
+      int t_lo = 0, t_hi = 0;
+      if (row_fast) {
+        t_lo = min(t_img, max(0, (r - xo + 7) >> 3));
+        t_hi = max(t_lo, min(t_img, (w - r - xo) >> 3));        // floor((w - 8 - r - xo) / 8) + 1, arithmetic shift
+      }
+      int t = 0;
+#pragma unroll 1
+      for (int seg = 0; seg < 2; seg++) {
+        const int t_end = seg == 0 ? t_lo : t_img;
+#pragma unroll 1
+        for (; t < t_end; t++) step8(t, std::integral_constant<int, 0>{});
+        if (seg == 0) {
+          if (mulhi) {
+#pragma unroll 2
+            for (; t < t_hi; t++) step8(t, std::integral_constant<int, 2>{});
+          } else {
+#pragma unroll 2
+            for (; t < t_hi; t++) step8(t, std::integral_constant<int, 1>{});
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- copy-out: lane = 8 columns
+    const int nrows = min(32, ye - yc);
+    if (out_lane) {
+      const uint32_t *orow = cs + 2 + ((8 * lane - R8) >> 2);
+      uint8_t *qo = out + (size_t)yc * w + x0;
+      const uint8_t *qc = frame + (size_t)yc * w + x0;
+      const unsigned wu = (unsigned)w;
+      auto put_row = [&](int j) {
+        uint2 o = *reinterpret_cast<const uint2 *>(orow + j * BM_PITCH);
+        if (ADAPTIVE) {
+          // dst = src > (int)mean - c ? 255 : 0 (reference :244-245), see box_finish
+          const uint2 sp = __ldg(reinterpret_cast<const uint2 *>(qc + (size_t)j * wu));
+          const uint32_t e0 = prmt(sp.x, 0, 0x4140) + kc - prmt(o.x, 0, 0x4140);
+          const uint32_t e1 = prmt(sp.x, 0, 0x4342) + kc - prmt(o.x, 0, 0x4342);
+          const uint32_t e2 = prmt(sp.y, 0, 0x4140) + kc - prmt(o.y, 0, 0x4140);
+          const uint32_t e3 = prmt(sp.y, 0, 0x4342) + kc - prmt(o.y, 0, 0x4342);
+          o.x = prmt_raw(e0, e1, 0xFDB9);
+          o.y = prmt_raw(e2, e3, 0xFDB9);
+        }
+        st_cs_u2(qo + (size_t)j * wu, o);
+      };
+      if (nrows == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) put_row(j);
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < nrows; j++) put_row(j);
+      }
+    }
+  }
+}
+
+// M = ceil(2^32 / count) with floor(S * M / 2^32) == S / count for every S <= 255 * count (r <= 31)
+static bool box_mid_mulhi(unsigned count, unsigned *M) {
+  const unsigned long long m = ((1ull << 32) + count - 1) / count;
+  const unsigned long long e = m * count - (1ull << 32);
+  if (m >= (1ull << 32) || 255ull * count * e >= (1ull << 32)) return false;
+  *M = (unsigned)m;
+  return true;
+}
+
 // k, m for the exact interior division of k_box_wide: floor(S * m / 2^k) == S / count for every S <= 255 * count
 static bool box_wide_magic(unsigned count, float *minv) {
   int lg = 0;
@@ -678,6 +979,44 @@ static int launch_box(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, 
     const int fast_ok = (r <= 63 && box_wide_magic((2 * r + 1) * (2 * r + 1), &minv)) ? 1 : 0;
     const bool aligned = w % 8 == 0 && reinterpret_cast<uintptr_t>(src) % 8 == 0 && reinterpret_cast<uintptr_t>(dst) % 8 == 0;
     dim3 grid((strips + 3) / 4, gy, n);
+    static const bool use_mid = [] { const char *e = getenv("GS_B200_BOX"); return !(e && e[0] == 'w'); }();   // A/B hook: "wide"
+    if (aligned && use_mid) {
+      // k_box_mid: chunks of 32 rows, so bands are multiples of 32 rows.  Short bands keep the grid many waves deep
+      // (3 CTAs of 4 warps per SM); a band re-reads 2r + 1 + 12 rows of its upper neighbour (L2 hits) and spends ~7
+      // instructions on each, against ~75 per regular row: the largest of 128 / 64 / 32 rows that still gives
+      // four waves, but not below 4r rows.
+      const long long four_waves = 148ll * 13 * 4;
+      BH = 32;
+      for (int cand = 128; cand >= 32; cand >>= 1)
+        if ((long long)strips * ((h + cand - 1) / cand) * n >= four_waves || cand == 32) { BH = cand; break; }
+      while (BH < 4 * (int)r && BH < 256) BH <<= 1;
+      static const int bh_env = [] { const char *e = getenv("GS_B200_BOX_BH"); return e ? atoi(e) : 0; }();   // A/B hook
+      if (bh_env >= 32) BH = bh_env / 32 * 32;
+      const long long warps = (long long)strips * ((h + BH - 1) / BH);
+      GSB_ASSERT(warps < (1ll << 31));
+      grid = dim3((unsigned)warps, 1, n);
+      static const bool allow_mulhi = [] { const char *e = getenv("GS_B200_BOX_MULHI"); return !(e && e[0] == '0'); }();   // A/B hook
+      unsigned mulhi = 0;
+      if (!(allow_mulhi && fast_ok && box_mid_mulhi((2 * r + 1) * (2 * r + 1), &mulhi))) mulhi = 0;
+      static DeviceOnce once;
+      if (once.needed()) {
+        GSB_CHECK(cudaFuncSetAttribute(k_box_mid<0, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        GSB_CHECK(cudaFuncSetAttribute(k_box_mid<1, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        GSB_CHECK(cudaFuncSetAttribute(k_box_mid<2, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        GSB_CHECK(cudaFuncSetAttribute(k_box_mid<3, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        once.done();
+      }
+#define GSB_BM_LAUNCH(RMV) k_box_mid<RMV, ADAPTIVE><<<grid, 32, BM_SMEM, s>>>(dst, src, (int)w, (int)h, (int)r, R8, BH, strips, cparam, minv, fast_ok, mulhi)
+      switch (r & 3) {
+        case 0: GSB_BM_LAUNCH(0); break;
+        case 1: GSB_BM_LAUNCH(1); break;
+        case 2: GSB_BM_LAUNCH(2); break;
+        default: GSB_BM_LAUNCH(3); break;
+      }
+#undef GSB_BM_LAUNCH
+      GSB_LAUNCHED(1);
+      return 0;
+    }
     if (aligned)
       k_box_wide<ADAPTIVE, true><<<grid, 128, 0, s>>>(dst, src, (int)w, (int)h, (int)r, R8, BH, strips, cparam, minv, fast_ok);
     else

@@ -10,7 +10,7 @@ from grayskull_b200 import api
 g.lib().gs_b200_set_device(0)
 op = sys.argv[1]
 torch.manual_seed(1)
-if op in ("blur_sobel", "box15", "integral", "resize", "resize_odd", "blur5", "sobel"):
+if op in ("blur_sobel", "box15", "blur15", "integral", "resize", "resize_odd", "blur5", "sobel"):
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 32
     src = torch.randint(0, 256, (n, 4096, 4096), dtype=torch.uint8, device="cuda")
     out = torch.zeros_like(src)
@@ -18,6 +18,7 @@ if op in ("blur_sobel", "box15", "integral", "resize", "resize_odd", "blur5", "s
         if op == "blur_sobel": api.blur_sobel_batch(src, 5, out=out)
         elif op == "blur5": api.blur_batch(src, 5, out=out)
         elif op == "sobel": api.sobel_batch(src, out=out)
+        elif op == "blur15": api.blur_batch(src, 15, out=out)
         elif op == "box15": api.adaptive_threshold_batch(src, 15, 5, out=out)
         elif op == "integral": ii = api.integral_batch(src)
         elif op == "resize": api.resize_batch(src, 2048, 2048)
