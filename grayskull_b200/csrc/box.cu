@@ -27,6 +27,8 @@
 //      inside the image use compile-time constants for count = (2r+1)^2 on a branch-free path,
 //      clipped pixels a 226-entry table.
 // Other radii / widths take the generic kernel (one thread per pixel, any radius).
+#include <string.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -651,8 +653,8 @@ __device__ __forceinline__ uint32_t dp2a_elem(uint32_t acc, uint2 a, uint2 b, in
 
 template <int RM, bool ADAPTIVE>
 __global__ void __launch_bounds__(32)
-k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int h, int r, int R8, int BH,
-          int strips, int cparam, float minv, int fast_ok, unsigned mulhi) {
+k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+          int w, int h, int r, int R8, int BH, int strips, int cparam, float minv, int fast_ok) {
   // one warp per CTA: the warps never synchronise with each other, and a 4-warp CTA held its 66 KB until its slowest
   // warp had finished (7 of 12 warp slots occupied on average in the first capture)
   extern __shared__ __align__(16) uint32_t bm_smem[];
@@ -693,6 +695,19 @@ k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int
       for (int k = 0; k < 4; k++) v[k] = ld_row(y + k);
     }
   };
+  // one lane asks the TMA unit to pull a 288-byte x 32-row box of source rows into L2 (no shared-memory destination):
+  // the entering rows a whole chunk before the register ring asks for them (the leaving rows were read 2r+1 rows
+  // earlier and are L2 hits anyway).  One instruction per chunk; the per-row prefetch.global.L2 form cost 4.5
+  // instructions per row for the same effect.
+  auto pf_box = [&](int y) {
+    if (use_tpf && lane == 0 && y < h) {
+      const int xw = (max(xs, 0) >> 2) & ~3;
+      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(&tmap), "r"(xw), "r"(y),
+                   "r"((int)blockIdx.z)
+                   : "memory");
+    }
+  };
+  pf_box(yb + r + 13);
   // the rows that enter / leave the window, in batches of four row steps; a ring of four batches keeps the loads
   // three batches (12 rows) ahead of their use, also across the H-phase
   uint2 en[4][4], lv[4][4];
@@ -723,6 +738,7 @@ k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int
   for (int yc = yb; yc < ye; yc += 32) {
     // ---- V-phase: C rows of image rows yc .. yc+31
     __syncwarp();                                               // the previous chunk's copy-out is done
+    pf_box(yc + r + 13 + 32 * use_tpf);                         // what the next chunk's ring loads will ask for (use_tpf: chunks ahead)
     auto v_phase = [&](auto guard_tag) {
       uint32_t *crow = cs + 2 + 4 * lane;
 #pragma unroll 1
@@ -777,34 +793,39 @@ k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int
       const uint2 *pe = grp + ge0 + 1, *pl = grp + gl0 + 1;
       uint2 *po = reinterpret_cast<uint2 *>(rw + 2);
       const int xo = xs + R8;                                   // image column of this row's first output
-      // eight outputs per step.  MODE 0: clipped windows (per-pixel count); 1: unclipped, magic multiplier on the FMA
-      // pipe; 2: unclipped, 32-bit multiply-high (r <= 31).  The window sums of a group of four are W + D_k with the
-      // D_k chained from zero: the chains of different groups are independent (the single chain W(c) = W(c-1) + .. - ..
-      // left a warp waiting 4 cycles on every IDP), only one add per group is serial.  The groups of the NEXT step are
-      // loaded before this step's arithmetic (the compiler cannot hoist them over the store of the outputs, which
-      // aliases the row as far as it can tell; they lie beyond byte 16 + 8t, see the header).
-      uint2 En[2] = {pe[0], pe[1]}, Ln[2] = {pl[0], pl[1]};
-      auto step8 = [&](int t, auto mode_tag) {
-        constexpr int MODE = decltype(mode_tag)::value;
-        const uint2 Ec[2] = {En[0], En[1]}, Lc[2] = {Ln[0], Ln[1]};
-        En[0] = pe[2 * t + 2], En[1] = pe[2 * t + 3], Ln[0] = pl[2 * t + 2], Ln[1] = pl[2 * t + 3];
+      // eight outputs per step; FAST: unclipped windows, magic multiplier; else per-pixel counts.  The window sums of a
+      // group of four are W + D_k with the D_k chained from zero: the chains of different groups are independent (the
+      // single chain W(c) = W(c-1) + .. - .. left a warp waiting 4 cycles on every IDP), only one add per group is
+      // serial.  The four groups a step consumes were loaded during the PREVIOUS step into the other of two register
+      // sets (A, B); volatile ld / st keep that order (the output store aliases the row as far as the compiler can
+      // tell, and with plain loads it sank them to the end of the step, right in front of their first use).
+      const uint32_t pe_s = smem_u32(pe), pl_s = smem_u32(pl), po_s = smem_u32(po);
+      auto lds2 = [](uint32_t addr) -> uint2 {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+        return v;
+      };
+      uint2 EA[2] = {lds2(pe_s), lds2(pe_s + 8)}, LA[2] = {lds2(pl_s), lds2(pl_s + 8)}, EB[2], LB[2];
+      EB[1] = E0, LB[1] = L0;                                   // "the group before A[0]"
+      // one step: consumes Ec / Lc (carry-in: the group before them, Ep / Lp), loads the next step's groups into Ex / Lx
+      auto step8 = [&](int t, auto fast_tag, const uint2 (&Ec)[2], const uint2 (&Lc)[2], const uint2 Ep, const uint2 Lp,
+                       uint2 (&Ex)[2], uint2 (&Lx)[2]) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        Ex[0] = lds2(pe_s + 16 * t + 16), Lx[0] = lds2(pl_s + 16 * t + 16);
+        Ex[1] = lds2(pe_s + 16 * t + 24), Lx[1] = lds2(pl_s + 16 * t + 24);
         uint32_t ow[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-          const uint2 E1 = Ec[s], L1 = Lc[s];
+          const uint2 Ea = s == 0 ? Ep : Ec[0], La = s == 0 ? Lp : Lc[0];
           uint32_t Wk[4], q[4], D = 0;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            D = dp2a_elem<false>(D, E0, E1, RM + k);
-            D = dp2a_elem<true>(D, L0, L1, LM + k);
+            D = dp2a_elem<false>(D, Ea, Ec[s], RM + k);
+            D = dp2a_elem<true>(D, La, Lc[s], LM + k);
             Wk[k] = W + D;
           }
           W = Wk[3];
-          E0 = E1, L0 = L1;
-          if (MODE == 2) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) q[k] = __umulhi(Wk[k], mulhi);
-          } else if (MODE == 1) {
+          if (FAST) {
 #pragma unroll
             for (int k = 0; k < 4; k++) q[k] = __float_as_uint(__fmaf_rd((float)Wk[k], minv, 8388608.0f));
           } else {
@@ -823,7 +844,14 @@ k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int
           }
           ow[s] = pack4_alu(q[0], q[1], q[2], q[3]);
         }
-        po[t] = make_uint2(ow[0], ow[1]);
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(po_s + 8 * t), "r"(ow[0]), "r"(ow[1]) : "memory");
+      };
+      // between loops the live set is A with the group before it in B[1]
+      auto single = [&](int t, auto fast_tag) {
+        step8(t, fast_tag, EA, LA, EB[1], LB[1], EB, LB);
+        const uint2 e1 = EA[1], l1 = LA[1];
+        EA[0] = EB[0], EA[1] = EB[1], LA[0] = LB[0], LA[1] = LB[1];
+        EB[1] = e1, LB[1] = l1;
       };
       // steps that reach into the image: [0, t_img); of those, [t_lo, t_hi) are fast: xo + 8t - r >= 0 and
       // xo + 8t + 7 + r <= w - 1
@@ -838,15 +866,14 @@ k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int
       for (int seg = 0; seg < 2; seg++) {
         const int t_end = seg == 0 ? t_lo : t_img;
 #pragma unroll 1
-        for (; t < t_end; t++) step8(t, std::integral_constant<int, 0>{});
+        for (; t < t_end; t++) single(t, std::false_type{});
         if (seg == 0) {
-          if (mulhi) {
-#pragma unroll 2
-            for (; t < t_hi; t++) step8(t, std::integral_constant<int, 2>{});
-          } else {
-#pragma unroll 2
-            for (; t < t_hi; t++) step8(t, std::integral_constant<int, 1>{});
+#pragma unroll 1
+          for (; t + 1 < t_hi; t += 2) {                        // A -> B -> A: no register rotation
+            step8(t, std::true_type{}, EA, LA, EB[1], LB[1], EB, LB);
+            step8(t + 1, std::true_type{}, EB, LB, EA[1], LA[1], EA, LA);
           }
+          if (t < t_hi) single(t++, std::true_type{});
         }
       }
     }
@@ -881,15 +908,6 @@ k_box_mid(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, int
       }
     }
   }
-}
-
-// M = ceil(2^32 / count) with floor(S * M / 2^32) == S / count for every S <= 255 * count (r <= 31)
-static bool box_mid_mulhi(unsigned count, unsigned *M) {
-  const unsigned long long m = ((1ull << 32) + count - 1) / count;
-  const unsigned long long e = m * count - (1ull << 32);
-  if (m >= (1ull << 32) || 255ull * count * e >= (1ull << 32)) return false;
-  *M = (unsigned)m;
-  return true;
 }
 
 // k, m for the exact interior division of k_box_wide: floor(S * m / 2^k) == S / count for every S <= 255 * count
@@ -995,9 +1013,10 @@ static int launch_box(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, 
       const long long warps = (long long)strips * ((h + BH - 1) / BH);
       GSB_ASSERT(warps < (1ll << 31));
       grid = dim3((unsigned)warps, 1, n);
-      static const bool allow_mulhi = [] { const char *e = getenv("GS_B200_BOX_MULHI"); return !(e && e[0] == '0'); }();   // A/B hook
-      unsigned mulhi = 0;
-      if (!(allow_mulhi && fast_ok && box_mid_mulhi((2 * r + 1) * (2 * r + 1), &mulhi))) mulhi = 0;
+      CUtensorMap pmap;
+      static const int tpf_env = [] { const char *e = getenv("GS_B200_BOX_TPF"); return e ? atoi(e) : 1; }();   // A/B hook: 0 = off, k = k chunks ahead
+      int use_tpf = (tpf_env > 0 && make_tmap_u8frames(&pmap, src, w, h, n, 72, 32)) ? tpf_env : 0;   // needs w % 16 == 0 and a 16-byte aligned base
+      if (!use_tpf) memset(&pmap, 0, sizeof(pmap));
       static DeviceOnce once;
       if (once.needed()) {
         GSB_CHECK(cudaFuncSetAttribute(k_box_mid<0, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
@@ -1006,7 +1025,7 @@ static int launch_box(uint8_t *dst, const uint8_t *src, unsigned w, unsigned h, 
         GSB_CHECK(cudaFuncSetAttribute(k_box_mid<3, ADAPTIVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
         once.done();
       }
-#define GSB_BM_LAUNCH(RMV) k_box_mid<RMV, ADAPTIVE><<<grid, 32, BM_SMEM, s>>>(dst, src, (int)w, (int)h, (int)r, R8, BH, strips, cparam, minv, fast_ok, mulhi)
+#define GSB_BM_LAUNCH(RMV) k_box_mid<RMV, ADAPTIVE><<<grid, 32, BM_SMEM, s>>>(pmap, use_tpf, dst, src, (int)w, (int)h, (int)r, R8, BH, strips, cparam, minv, fast_ok)
       switch (r & 3) {
         case 0: GSB_BM_LAUNCH(0); break;
         case 1: GSB_BM_LAUNCH(1); break;
