@@ -597,23 +597,35 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
 // k_box_wide pays ~37 lane-instructions per pixel: a 256-column prefix scan per row (shuffles + selects) and
 // two scattered LDS per pixel.  This form keeps the same warp-autonomous 256-column segments and the same
 // rolling u16x2 column sums, but turns the horizontal pass into a ROLLING sum too, by transposing through
-// shared memory: a warp alternates between
+// shared memory.  One warp per CTA (the warps never synchronise with each other; 16.3 KB each, 13 per SM)
+// alternates between
 //   V-phase : 32 rows; lanes = 8 columns each.  The column sums of a row (256 u16) go to the warp's private
-//             C tile [32 rows][4 u16 pad + 256 u16], pitch 130 words;
-//   H-phase : lanes = ROWS.  Lane j walks row j from left to right with the window sum in one register:
-//             W(c) = W(c-1) + C[c+r] - C[c-r-1], each term one IDP.2A (dp2a reads either 16-bit half of a
-//             pair word through its byte multiplier: 0x0001 / 0x0100 add, 0x00FF / 0xFF00 subtract), the C
-//             values come as 64-bit groups of four (pitch = 2 mod 32 words: conflict-free with lanes on rows);
-//             r mod 4 fixes where the entering / leaving elements sit inside their groups, hence the template
-//             parameter.  Quotients as in k_box_wide.  The 8 output bytes of an iteration overwrite the head
-//             of the lane's own C row (already consumed: byte 16+8t <= 8*(gl0+2t+3));
+//             C tile [32 rows][4 u16 pad + 256 u16], pitch 130 words.  Source rows come straight from global
+//             memory through a register ring of four 4-row batches (loads 12 rows ahead of their use, also
+//             across the H-phase); one lane asks the TMA unit to prefetch the next chunk's rows into L2
+//             (UTMAPF.L2, no shared-memory destination): without it the DRAM latency of the entering rows was
+//             not covered (0.37 -> 0.46 of the HBM roofline);
+//   H-phase : lanes = ROWS.  Lane j walks row j from left to right: the window sums of four neighbouring outputs
+//             are W + D_k, D_k = sum_{i<=k} C[c+i+r] - C[c+i-r-1] chained from zero, each term one IDP.2A (dp2a
+//             reads either 16-bit half of a pair word through its byte multiplier: 0x0001 / 0x0100 add, 0x00FF /
+//             0xFF00 subtract); the chains of different groups are independent, W advances once per group.  The C
+//             values come as 64-bit groups of four (pitch = 2 mod 32 words: conflict-free with lanes on rows); r mod
+//             4 fixes where the entering / leaving elements sit inside their groups, hence the template
+//             parameter.  Quotients as in k_box_wide (clipped counts: MUFU.RCP quotient + integer remainder
+//             check instead of the IEEE-division subroutine).  The 8 output bytes of a step overwrite the head of
+//             the lane's own C row (already consumed: byte 16+8t <= 8*(gl0+2t+3)); a lane never reads or writes
+//             another lane's row (racecheck-clean);
 //   copy-out: lanes = columns again; rows leave as coalesced 64-bit stores (gs_adaptive_threshold compares
 //             with the centre pixels here, on 16-bit lane pairs).
-// ~10 lane-instructions per pixel instead of ~37; global loads are prefetched 4..8 rows ahead and the
-// batch for the next chunk is in flight during the H-phase.
+// 13.5 lane-instructions per pixel instead of ~37 (ncu); blur r = 9 / 15 / 31 at 0.47 / 0.46 / 0.42 of the HBM
+// roofline against 0.23 / 0.23 / 0.21 (profiles/r02_ab_box.txt has every step of the way).
+#ifndef GSB_BM_UNROLL
+#define GSB_BM_UNROLL 1
+#endif
 #ifndef GSB_BM_PF
 #define GSB_BM_PF 0                         // L2 prefetch of the entering rows a chunk ahead: +3 % time saved, +3.6 % instructions: a wash
 #endif
+constexpr int BM_UNROLL = GSB_BM_UNROLL;
 constexpr int BM_PITCH = 130;                       // words per C row
 constexpr int BM_WARP_WORDS = 32 * BM_PITCH + 8;    // + the look-ahead groups of the last row
 constexpr int BM_SMEM = BM_WARP_WORDS * 4;         // one warp per CTA: 16.3 KB, 13 CTAs per SM
@@ -655,8 +667,8 @@ template <int RM, bool ADAPTIVE>
 __global__ void __launch_bounds__(32)
 k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
           int w, int h, int r, int R8, int BH, int strips, int cparam, float minv, int fast_ok) {
-  // one warp per CTA: the warps never synchronise with each other, and a 4-warp CTA held its 66 KB until its slowest
-  // warp had finished (7 of 12 warp slots occupied on average in the first capture)
+  // one warp per CTA: a 4-warp CTA held its 66 KB until its slowest warp had finished (7 of 12 warp slots occupied on
+  // average in the first ncu capture)
   extern __shared__ __align__(16) uint32_t bm_smem[];
   constexpr int LM = (3 - RM) & 3;
   const int lane = threadIdx.x;
@@ -707,7 +719,7 @@ k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__rest
                    : "memory");
     }
   };
-  pf_box(yb + r + 13);
+  pf_box(yb - r), pf_box(yb - r + 32), pf_box(yb - r + 64);     // the band's first rows (window build-up and ring prologue) arrive together
   // the rows that enter / leave the window, in batches of four row steps; a ring of four batches keeps the loads
   // three batches (12 rows) ahead of their use, also across the H-phase
   uint2 en[4][4], lv[4][4];
@@ -807,12 +819,18 @@ k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__rest
       };
       uint2 EA[2] = {lds2(pe_s), lds2(pe_s + 8)}, LA[2] = {lds2(pl_s), lds2(pl_s + 8)}, EB[2], LB[2];
       EB[1] = E0, LB[1] = L0;                                   // "the group before A[0]"
+      const int u_in = (60 - ge0) >> 1;                         // t <= u_in: groups ge0 + 2t + 3, ge0 + 2t + 4 (step t+1's) are <= 64, the row's last
       // one step: consumes Ec / Lc (carry-in: the group before them, Ep / Lp), loads the next step's groups into Ex / Lx
-      auto step8 = [&](int t, auto fast_tag, const uint2 (&Ec)[2], const uint2 (&Lc)[2], const uint2 Ep, const uint2 Lp,
-                       uint2 (&Ex)[2], uint2 (&Lx)[2]) {
+      auto step8 = [&](int t, auto fast_tag, auto guard_tag, const uint2 (&Ec)[2], const uint2 (&Lc)[2], const uint2 Ep,
+                       const uint2 Lp, uint2 (&Ex)[2], uint2 (&Lx)[2]) {
         constexpr bool FAST = decltype(fast_tag)::value;
-        Ex[0] = lds2(pe_s + 16 * t + 16), Lx[0] = lds2(pl_s + 16 * t + 16);
-        Ex[1] = lds2(pe_s + 16 * t + 24), Lx[1] = lds2(pl_s + 16 * t + 24);
+        Lx[0] = lds2(pl_s + 16 * t + 16), Lx[1] = lds2(pl_s + 16 * t + 24);
+        if (!decltype(guard_tag)::value || t <= u_in) {                                        // both entering groups of step t+1 lie inside this lane's row
+          Ex[0] = lds2(pe_s + 16 * t + 16), Ex[1] = lds2(pe_s + 16 * t + 24);
+        } else {                                                // at the end of the row: never read the neighbouring lane's row
+          Ex[0] = ge0 + 2 * t + 3 <= 64 ? lds2(pe_s + 16 * t + 16) : make_uint2(0u, 0u);
+          Ex[1] = make_uint2(0u, 0u);
+        }
         uint32_t ow[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -848,7 +866,7 @@ k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__rest
       };
       // between loops the live set is A with the group before it in B[1]
       auto single = [&](int t, auto fast_tag) {
-        step8(t, fast_tag, EA, LA, EB[1], LB[1], EB, LB);
+        step8(t, fast_tag, std::true_type{}, EA, LA, EB[1], LB[1], EB, LB);
         const uint2 e1 = EA[1], l1 = LA[1];
         EA[0] = EB[0], EA[1] = EB[1], LA[0] = LB[0], LA[1] = LB[1];
         EB[1] = e1, LB[1] = l1;
@@ -868,12 +886,13 @@ k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__rest
 #pragma unroll 1
         for (; t < t_end; t++) single(t, std::false_type{});
         if (seg == 0) {
-#pragma unroll 1
-          for (; t + 1 < t_hi; t += 2) {                        // A -> B -> A: no register rotation
-            step8(t, std::true_type{}, EA, LA, EB[1], LB[1], EB, LB);
-            step8(t + 1, std::true_type{}, EB, LB, EA[1], LA[1], EA, LA);
+#pragma unroll BM_UNROLL
+          for (; t + 1 < t_hi && t + 1 <= u_in; t += 2) {       // A -> B -> A: no register rotation; look-ahead inside the row
+            step8(t, std::true_type{}, std::false_type{}, EA, LA, EB[1], LB[1], EB, LB);
+            step8(t + 1, std::true_type{}, std::false_type{}, EB, LB, EA[1], LA[1], EA, LA);
           }
-          if (t < t_hi) single(t++, std::true_type{});
+#pragma unroll 1
+          for (; t < t_hi; t++) single(t, std::true_type{});    // the last one or two steps of the row: guarded look-ahead
         }
       }
     }
@@ -900,8 +919,27 @@ k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__rest
         st_cs_u2(qo + (size_t)j * wu, o);
       };
       if (nrows == 32) {
+        if (ADAPTIVE) {
+          // the centre rows (L2 hits: they entered the window r+1 rows ago), eight loads in flight
 #pragma unroll
-        for (int j = 0; j < 32; j++) put_row(j);
+          for (int j0 = 0; j0 < 32; j0 += 8) {
+            uint2 sp[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) sp[j] = __ldg(reinterpret_cast<const uint2 *>(qc + (size_t)(j0 + j) * wu));
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              uint2 o = *reinterpret_cast<const uint2 *>(orow + (j0 + j) * BM_PITCH);
+              const uint32_t e0 = prmt(sp[j].x, 0, 0x4140) + kc - prmt(o.x, 0, 0x4140);
+              const uint32_t e1 = prmt(sp[j].x, 0, 0x4342) + kc - prmt(o.x, 0, 0x4342);
+              const uint32_t e2 = prmt(sp[j].y, 0, 0x4140) + kc - prmt(o.y, 0, 0x4140);
+              const uint32_t e3 = prmt(sp[j].y, 0, 0x4342) + kc - prmt(o.y, 0, 0x4342);
+              st_cs_u2(qo + (size_t)(j0 + j) * wu, make_uint2(prmt_raw(e0, e1, 0xFDB9), prmt_raw(e2, e3, 0xFDB9)));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) put_row(j);
+        }
       } else {
 #pragma unroll 1
         for (int j = 0; j < nrows; j++) put_row(j);

@@ -849,7 +849,7 @@ def test_wide_radius_box_vs_oracle_and_reference_goldens(G, O):
         frames = np.stack([rng.integers(0, 256, (h, w)).astype(np.uint8), L.natural_like(w, h, 8),
                            np.full((h, w), 255, np.uint8)])
         src = dev(frames)
-        for r in (8, 9, 12, 15, 16, 31, 63, 64, 100, 120, 121, 300):
+        for r in (8, 9, 10, 12, 13, 15, 16, 17, 22, 31, 63, 64, 100, 120, 121, 300):   # r mod 4 = 0..3: the four k_box_mid instantiations
             if r > 31 and w * h > 200000:
                 continue                       # the oracle's cost grows with r
             gb = G.blur_batch(src, r).cpu().numpy()

@@ -7,7 +7,5 @@ import json,sys; d=json.loads(sys.stdin.read())
 for k in ('gs_blur_r7','gs_blur_r9','gs_blur_r15','gs_blur_r31','gs_adaptive_threshold_r5','gs_adaptive_threshold_r15'):
     print('%-8s %-28s %.3f ms  %.3f' % ('$1', k, d['kernels'][k]['ms'], d['kernels'][k]['frac']))"; }
 run mid
-GS_B200_BOX_TPF=0 run notpf
-GS_B200_BOX_TPF=2 run tpf2
 for v in "$@"; do [ -f grayskull_b200/libv_$v.so ] && GS_B200_LIB=$PWD/grayskull_b200/libv_$v.so run $v; done
 [ -n "$AB_WIDE" ] && GS_B200_BOX=wide run wide
