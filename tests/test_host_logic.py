@@ -204,6 +204,82 @@ def test_wide_box_division_is_exact():
             assert np.array_equal(got, S // d), (d, f)
 
 
+def _box_mid_row_model(C, r, R8, w_img, xs, look_ahead=True):
+    """One H-phase row of box.cu k_box_mid, restated on a byte buffer: the row of 256 u16 column sums is laid out as the
+    V-phase stores it (4 u16 of zero pad, then groups of four columns as two pair words (c0,c2) (c1,c3)); the walk reads
+    64-bit groups, forms W + D_k through the (word, half) selection of dp2a_elem, and writes the 8 output sums of step t
+    over bytes [8 + 8t, 16 + 8t) of the SAME buffer -- with the next step's groups read BEFORE that store, as the kernel
+    orders them.  Returns the window sums of the steps that reach into the image."""
+    buf = np.zeros(130 * 4, np.uint8)
+    u16 = buf.view(np.uint16)
+    for l in range(32):                                          # V-phase store of lane l: words 2 + 4l .. 5 + 4l
+        c = C[8 * l: 8 * l + 8]
+        u16[4 + 8 * l: 12 + 8 * l] = [c[0], c[2], c[1], c[3], c[4], c[6], c[5], c[7]]
+    RM, LM = r & 3, (3 - (r & 3)) & 3
+    ge0, gl0 = (R8 + r + 4) >> 2, (R8 - r + 3) >> 2
+    outw = 256 - 2 * R8
+    iters = outw >> 3
+
+    def grp(g):                                                  # a 64-bit group: four u16 in storage order
+        assert 0 <= g <= 64, ("group outside the lane's row", g)
+        return buf[8 * g: 8 * g + 8].view(np.uint16).copy()
+
+    def elem(a, b, idx):                                         # dp2a_elem: word idx & 1, half (idx >> 1) & 1 of group a / b
+        g = a if idx < 4 else b
+        return int(g[2 * (idx & 1) + ((idx >> 1) & 1)])
+    L0, E0 = grp(gl0), grp(ge0)
+    W = sum(elem(L0, L0, k) for k in range(LM, 4)) + sum(int(grp(g).sum()) for g in range(gl0 + 1, ge0)) + \
+        sum(elem(E0, E0, k) for k in range(RM))
+    xo = xs + R8
+    t_img = min(iters, (w_img - xo + 7) >> 3)
+    u_in = (60 - ge0) >> 1
+    out = []
+    EA, LA = [grp(ge0 + 1), grp(ge0 + 2)], [grp(gl0 + 1), grp(gl0 + 2)]
+    Ep, Lp = E0, L0
+    zero = np.zeros(4, np.uint16)
+    for t in range(t_img):
+        # look-ahead of step t+1, guarded exactly like the kernel's tail steps (the unguarded loop runs while t + 1 <= u_in)
+        Ln = [grp(gl0 + 2 * t + 3), grp(gl0 + 2 * t + 4)]
+        if t <= u_in:
+            En = [grp(ge0 + 2 * t + 3), grp(ge0 + 2 * t + 4)]
+        else:
+            En = [grp(ge0 + 2 * t + 3) if ge0 + 2 * t + 3 <= 64 else zero, zero]
+        sums = []
+        for s_ in range(2):
+            Ea, La = (Ep, Lp) if s_ == 0 else (EA[0], LA[0])
+            D = 0
+            for k in range(4):
+                D += elem(Ea, EA[s_], RM + k) - elem(La, LA[s_], LM + k)
+                sums.append(W + D)
+            W += D
+        out.append(sums)
+        buf[8 + 8 * t: 16 + 8 * t] = 0xAB                        # the packed quotients overwrite the consumed head of the row
+        Ep, Lp, EA, LA = EA[1], LA[1], En, Ln
+    return np.array(out, np.int64).reshape(-1)
+
+
+def test_box_mid_row_walk_matches_direct_window_sums():
+    """box.cu k_box_mid, H-phase index arithmetic (r mod 4 element positions, permuted pair layout, first / last groups,
+    in-place output store, look-ahead guards) against direct window sums, for every radius the kernel takes and strips at
+    the left edge, in the interior and hanging over the right edge of the image"""
+    rng = np.random.default_rng(5)
+    for r in list(range(8, 41)) + [47, 48, 63, 64, 77, 100, 119, 120]:
+        R8 = (r + 7) // 8 * 8
+        outw = 256 - 2 * R8
+        assert outw >= 16
+        for w_img in (outw * 3 + 40, 4096, 8 * ((r + 9) // 8)):
+            strips = (w_img + outw - 1) // outw
+            for strip in sorted({0, strips // 2, strips - 1}):
+                xs = strip * outw - R8
+                cols = np.arange(xs, xs + 256)
+                C = np.where((cols >= 0) & (cols < w_img), rng.integers(0, (2 * r + 1) * 255 + 1, 256), 0).astype(np.int64)
+                got = _box_mid_row_model(C, r, R8, w_img, xs)
+                Cp = np.concatenate([np.zeros(r + 1, np.int64), C, np.zeros(r + 1, np.int64)])
+                want = np.array([Cp[c + 1: c + 2 * r + 2].sum() for c in range(R8, R8 + len(got))])
+                assert np.array_equal(got, want), (r, w_img, strip)
+                assert len(got) >= min(outw, w_img - (xs + R8)), (r, w_img, strip)   # every in-image output is produced
+
+
 def test_filter_magic_division_is_exact():
     """filter.cu fast path: for norm >= 2, min(255, umulhi((u32)sum, floor(2^32/norm)+1)) equals the reference's
     `sum = sum / norm` (int converted to unsigned, quotient back to int, clamp 0..255) for every sum the host check
