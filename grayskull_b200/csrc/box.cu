@@ -619,6 +619,9 @@ k_box_wide(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int w, in
 //             with the centre pixels here, on 16-bit lane pairs).
 // 13.5 lane-instructions per pixel instead of ~37 (ncu); blur r = 9 / 15 / 31 at 0.47 / 0.46 / 0.42 of the HBM
 // roofline against 0.23 / 0.23 / 0.21 (profiles/r02_ab_box.txt has every step of the way).
+#ifndef GSB_BM_PACK_IMAD
+#define GSB_BM_PACK_IMAD 0                  // 1: byte packing by two IMAD + one PRMT instead of three PRMT (A/B hook)
+#endif
 #ifndef GSB_BM_UNROLL
 #define GSB_BM_UNROLL 1
 #endif
@@ -860,7 +863,11 @@ k_box_mid(const __grid_constant__ CUtensorMap tmap, int use_tpf, uint8_t *__rest
               q[k] = q0 & 0xFFu;
             }
           }
+#if GSB_BM_PACK_IMAD
+          ow[s] = pack4(q[0], q[1], q[2], q[3]);
+#else
           ow[s] = pack4_alu(q[0], q[1], q[2], q[3]);
+#endif
         }
         asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(po_s + 8 * t), "r"(ow[0]), "r"(ow[1]) : "memory");
       };
