@@ -386,6 +386,9 @@ k_deinterleave2(uint32_t *__restrict__ planes, const uint32_t *__restrict__ ii, 
 #ifndef GSB_LBP_ROWDIFF
 #define GSB_LBP_ROWDIFF 1                     // measured: 63.26 -> 62.35 ms per 32 UHD frames
 #endif
+#ifndef GSB_LBP3_GRAB
+#define GSB_LBP3_GRAB 0
+#endif
 #ifndef GSB_LBP3_FLAT
 #define GSB_LBP3_FLAT 8        // a warp with this many survivors or fewer switches to the (window, weak) flat mode
 #endif
@@ -396,7 +399,7 @@ constexpr int LBP3_HIT_WORDS = 128;              // mask words of a tile: at mos
 template <int LBP3_THREADS>
 __global__ void __launch_bounds__(LBP3_THREADS)
 k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int twx, int twy, int bw, int ph,
-            int tiles_x, int flat_n, unsigned *__restrict__ masks) {
+            int tiles_x, int flat_n, int grab, unsigned *__restrict__ masks) {
   extern __shared__ __align__(128) unsigned char lsm[];
   // two column-parity planes of bw x ph words each (see k_deinterleave2), 128-byte aligned
   const uint32_t plane_bytes = ((uint32_t)bw * ph * 4u + 127u) & ~127u;
@@ -406,6 +409,7 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
   // 128-byte aligned start of it): tile | barrier, counters, 64 hit words | tables | survivor lists
   unsigned char *ctl = lsm + ((tile_bytes + 127u) & ~127u);
   uint64_t &bar = *reinterpret_cast<uint64_t *>(ctl);
+  unsigned &next_slot = *reinterpret_cast<unsigned *>(ctl + 8);   // dynamic slot hand-out (grab > 0)
   unsigned *hit = reinterpret_cast<unsigned *>(ctl + 16);   // twy * (twx / 32) <= LBP3_HIT_WORDS mask words
   TileGeo *s_geo = reinterpret_cast<TileGeo *>(ctl + 640);
   Weak *s_weak = reinterpret_cast<Weak *>(s_geo + dc.nfeatures);
@@ -439,6 +443,7 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     for (int i = tid; i < dc.nsubsets; i += LBP3_THREADS) s_sub[i] = dc.subsets[i];
   }
   if (tid < LBP3_HIT_WORDS) hit[tid] = 0;
+  if (tid == 0) next_slot = 0;
   __syncthreads();
   mbar_wait(&bar, 0);
 
@@ -490,18 +495,25 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     }
     return true;
   };
-  // From here on every warp works alone on its own 32-window slots (slot = warp, warp + nwarps, ...): its
-  // survivors are re-packed into a warp-private list with ballots -- no shared counters, no CTA barrier until
-  // the masks are written -- so a warp that is stuck in a deep stage never holds the other fifteen up.
+  // From here on every warp works alone on 32-window slots: its survivors are re-packed into a warp-private list with
+  // ballots -- no shared counters inside the cascade, no CTA barrier until the masks are written -- so a warp that is
+  // stuck in a deep stage never holds the other fifteen up.  Which slots a warp takes: grab == 0: slot = warp,
+  // warp + nwarps, ... (static; a warp whose slots hold the faces of the tile finishes long after the others, and the CTA
+  // keeps its tile and warp slots until then: 24 of 32 warp slots occupied on average, ncu); grab > 0: `grab`
+  // consecutive slots at a time from a shared counter, taken through all stage groups before the next hand-out.
   constexpr int NWARPS = LBP3_THREADS / 32;
   const unsigned warp = tid >> 5, lt = (1u << lane) - 1u;
   const int nslots = nwin >> 5;
   const int cap = ((nslots + NWARPS - 1) / NWARPS) * 32;
+  const int take = min(grab, cap / 32);
+  const int sx_n = twx >> 5;
+  // slots sb, sb + stride, ... < se through the whole cascade, then their mask words to global memory
+  auto process = [&](int sb, int se, int stride) {
   uint16_t *cur = list_a + warp * cap, *nxt = list_a + (NWARPS + warp) * cap;
   unsigned n = 0;
   {
     const bool last = dc.ngroups == 1;
-    for (int slot = (int)warp; slot < nslots; slot += NWARPS) {
+    for (int slot = sb; slot < se; slot += stride) {
       const unsigned id = (unsigned)slot * 32u + lane;
       const int lx = (int)(id & (unsigned)(twx - 1)), ly = (int)(id >> shift);
       const bool valid = wx0 + lx < sc.nx && wy0 + ly < sc.ny;
@@ -574,14 +586,26 @@ k_lbp_scan3(const __grid_constant__ CUtensorMap tmap, DevCascade dc, int si, int
     uint16_t *t = cur;
     cur = nxt, nxt = t;
   }
-  // the warp's slots were touched by nobody else: store their mask words and leave -- no CTA barrier
+  // the slots were touched by nobody else: store their mask words -- no CTA barrier
   __syncwarp();
-  const int sx_n = twx >> 5;
-  for (int slot = (int)warp + (int)lane * NWARPS; slot < nslots; slot += 32 * NWARPS) {
+  for (int slot = sb + (int)lane * stride; slot < se; slot += 32 * stride) {
     const int ly = slot / sx_n, sx = slot % sx_n;
     const unsigned chunk = (unsigned)(wx0 >> 5) + (unsigned)sx;
     if (wy0 + ly < sc.ny && chunk < sc.chunks)
       masks[(size_t)f * dc.total_slots + sc.slot0 + (unsigned long long)(wy0 + ly) * sc.chunks + chunk] = hit[slot];
+  }
+  __syncwarp();
+  };
+  if (take <= 0) {
+    process((int)warp, nslots, NWARPS);
+  } else {
+    for (;;) {
+      int s0 = 0;
+      if (lane == 0) s0 = (int)atomicAdd(&next_slot, (unsigned)take);
+      s0 = __shfl_sync(0xFFFFFFFFu, s0, 0);
+      if (s0 >= nslots) break;
+      process(s0, min(s0 + take, nslots), 1);
+    }
   }
 }
 
@@ -968,6 +992,8 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
     GSB_CHECK(cudaMemsetAsync(masks, 0, 4 * (size_t)dc.total_slots * n, st));   // padding slots between scales
     int flat_n = GSB_LBP3_FLAT;
     if (const char *fe = getenv("GS_B200_LBP_FLAT")) flat_n = atoi(fe);
+    int grab = GSB_LBP3_GRAB;                 // slots per dynamic hand-out, 0 = static slot assignment
+    if (const char *ge = getenv("GS_B200_LBP_GRAB")) grab = atoi(ge);
     // frames go through in chunks so that the de-interleaved copy stays small (<= 1 GiB of workspace)
     const size_t frame_bytes = (size_t)iw * ih * 4;
     unsigned chunk = (unsigned)(((size_t)1 << 30) / frame_bytes);
@@ -988,10 +1014,10 @@ int gs_b200_lbp_detect_batch(const struct gs_lbp_cascade *c, const uint32_t *ii,
           return gsb::record_error(cudaErrorInvalidValue, __FILE__, __LINE__);
         if (tp.threads == gsb::LBP3_BIG_THREADS)
           gsb::k_lbp_scan3<gsb::LBP3_BIG_THREADS><<<dim3((unsigned)(tp.tiles_x * tp.tiles_y), nf), gsb::LBP3_BIG_THREADS, tp.smem, st>>>(
-              tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, masks + (size_t)f0 * dc.total_slots);
+              tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, grab, masks + (size_t)f0 * dc.total_slots);
         else
           gsb::k_lbp_scan3<gsb::LBP3_THREADS><<<dim3((unsigned)(tp.tiles_x * tp.tiles_y), nf), gsb::LBP3_THREADS, tp.smem, st>>>(
-              tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, masks + (size_t)f0 * dc.total_slots);
+              tm, dc, si, tp.twx, tp.twy, tp.bw, tp.ph, tp.tiles_x, flat_n, grab, masks + (size_t)f0 * dc.total_slots);
         GSB_LAUNCHED(1);
       }
     }
