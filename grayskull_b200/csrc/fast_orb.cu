@@ -67,6 +67,11 @@ static int brief_table_init() {
 // glibc 2.39 sinf (sysdeps/ieee754/flt-32/s_sinf.c, sincosf.h; double evaluation) and atan2f /
 // atanf (e_atan2f.c, s_atanf.c; float evaluation), restated with explicitly rounded ops.
 // tools/validate_trig.c checks the same restatement against libm exhaustively on the CPU.
+// Provenance: the polynomial coefficients, reduction constants and the order of operations follow the GNU C Library
+// (glibc 2.39, LGPL-2.1-or-later; sinf/sincosf: Copyright (C) the FSF, contributed by Arm; atanf / atan2f: the
+// fdlibm-derived float routines, Copyright (C) 1993 Sun Microsystems, "permission to use, copy, modify, and distribute
+// this software is freely granted, provided that this notice is preserved").  They are third-party numerics restated
+// because bit-exactness with the reference's libm calls leaves no freedom, not reference (grayskull) code.
 // ---------------------------------------------------------------------------------------------
 __device__ float dev_sinf(float y) {
   const double HPI_INV = 0x1.45F306DC9C883p+23, HPI = 0x1.921FB54442D18p0;
