@@ -143,6 +143,22 @@ def test_diff_stencils():
 
 
 @needs_ref
+def test_diff_box_medium_radii():
+    """the radii the GPU suite runs k_box_mid's four instantiations at (r mod 4 = 0..3), oracle against the compiled
+    reference on small ragged images: the GPU parity test for those radii compares with the oracle, so the oracle is
+    pinned there too (the round-2 goldens hold 8 / 9 / 11 / 15 / 31)"""
+    R = L.ref(); rng = np.random.default_rng(17)
+    for i, a in enumerate(_rand_images(rng, 24)):
+        h, w = a.shape
+        for r in (10, 12, 13, 16, 17, 22):
+            d = np.empty_like(a); R.gs_blur(L.img(d), L.img(a), r)
+            assert np.array_equal(d, o_blur(a, r)), ("blur", w, h, r)
+            c = int(rng.integers(-60, 60))
+            d = np.empty_like(a); R.gs_adaptive_threshold(L.img(d), L.img(a), r, c)
+            assert np.array_equal(d, o_adaptive(a, r, c)), ("adaptive", w, h, r, c)
+
+
+@needs_ref
 def test_diff_fast_orb():
     R = L.ref(); rng = np.random.default_rng(2)
     for i, a in enumerate(_rand_images(rng, 150, lo=7, hi=70)):
