@@ -149,6 +149,33 @@ def main():
             n1 = R.gs_lbp_detect(ref_c, L.ptr(i1), w, h, L.ptr(q1), mr, sf, mn, mx, st)
             n2 = O.gso_lbp_detect(cas.ptr, L.ptr(i2), w, h, L.ptr(q2), mr, sf, mn, mx, st)
             same("lbp_detect", q1[:n1], q2[:n2], (w, h, sf, mn, mx, st, mr))
+        # round-2 rows: blobs with and without label overflow, blob corners, perspective warps
+        # (degenerate quads included), orientation with radii whose float sums round
+        b = L.binary_like(w, h, int(rng.integers(0, 1 << 30)), density=float(rng.uniform(0.1, 0.9)), smooth=int(rng.integers(0, 4))) \
+            if rng.random() < 0.8 else a
+        for nb in (2000, int(rng.integers(1, 40))):
+            l1 = np.full(b.shape, 0x5555, np.uint16); l2 = l1.copy()
+            b1 = np.zeros(nb, L.BLOB_DTYPE); b2 = np.zeros(nb, L.BLOB_DTYPE)
+            m1 = R.gs_blobs(L.img(b), L.ptr(l1), L.ptr(b1), nb)
+            m2 = O.gso_blobs(L.ptr(b), w, h, L.ptr(l2), L.ptr(b2), nb)
+            same("blobs_labels", l1, l2, (w, h, nb)); same("blobs", L.blob_fields(b1[:m1]), L.blob_fields(b2[:m2]), (w, h, nb))
+            for j in range(min(m1, 3)):
+                c1, c2 = np.zeros((4, 2), np.uint32), np.zeros((4, 2), np.uint32)
+                R.gs_blob_corners(L.img(b), L.ptr(l1), L.ptr(b1[j:j + 1]), L.ptr(c1))
+                O.gso_blob_corners(L.ptr(b), w, h, L.ptr(l2), L.ptr(b2[j:j + 1]), L.ptr(c2))
+                same("blob_corners", c1, c2, (w, h, nb, j))
+        pw, ph = int(rng.integers(1, 80)), int(rng.integers(1, 80))
+        quad = rng.integers(0, max(w, h) + 20, (4, 2)).astype(np.uint32)
+        if rng.random() < 0.2:
+            quad[int(rng.integers(0, 4))] = quad[int(rng.integers(0, 4))]          # coincident corners
+        p1, p2 = np.empty((ph, pw), np.uint8), np.empty((ph, pw), np.uint8)
+        R.gs_perspective_correct(L.img(p1), L.img(a), L.ptr(quad)); O.gso_perspective_correct(L.ptr(p2), pw, ph, L.ptr(a), w, h, L.ptr(quad))
+        same("perspective", p1, p2, (w, h, pw, ph, quad.tolist()))
+        if w >= 3 and h >= 3:                                     # the reference asserts r <= x < w - r, r <= y < h - r
+            ro = int(rng.integers(1, (min(w, h) - 1) // 2 + 1))
+            ox, oy = int(rng.integers(ro, w - ro)), int(rng.integers(ro, h - ro))
+            same("orientation", np.float32(R.gs_compute_orientation(L.img(a), ox, oy, ro)).tobytes(),
+                 np.float32(O.gso_compute_orientation(L.ptr(a), w, h, ox, oy, ro)).tobytes(), (w, h, ox, oy, ro))
     print("no mismatch in %.0f s, seed %d:" % (time.time() - t0, seed), " ".join("%s=%d" % kv for kv in sorted(counts.items())))
 
 
