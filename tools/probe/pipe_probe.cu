@@ -26,6 +26,15 @@ __global__ void k(uint32_t *out, uint32_t seed, long long *cyc) {
       if (OP == 6) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(a[i]) : "r"(b));
       if (OP == 7) asm volatile("dp2a.lo.u32.s32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b), "r"(0x00FFu));
       if (OP == 8) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
+      if (OP == 9) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(seed));
+      if (OP == 10) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(seed));
+      if (OP == 11) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(1.0001f));
+      if (OP == 12) asm volatile("{ .reg .b16 lo, hi; .reg .f32 t; mov.b32 {lo, hi}, %0; cvt.rn.f32.u16 t, hi; mov.b32 %0, t; }" : "+r"(a[i]));
+      if (OP == 13) asm volatile("{ .reg .f32 t; mov.b32 t, %0; cvt.rzi.u32.f32 %0, t; }" : "+r"(a[i]));
+      if (OP == 14) asm volatile("popc.b32 %0, %0;" : "+r"(a[i]));
+      if (OP == 15) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
+      if (OP == 16) asm volatile("vadd2.u32.u32.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(seed));
+      if (OP == 17) asm volatile("max.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b));
     }
   }
   const long long t1 = clock64();
@@ -53,6 +62,7 @@ static void run(const char *name, int warps) {
 }
 #define ALL(OP, NAME) run<OP, 1>(NAME, 1); run<OP, 8>(NAME, 4); run<OP, 8>(NAME, 16); run<OP, 8>(NAME, 32);
 int main() {
-  ALL(0, "IDP.2A") ALL(7, "IDP.2A.S8") ALL(1, "IDP.4A") ALL(2, "IMAD") ALL(3, "IADD") ALL(4, "I2FP") ALL(5, "FFMA.RM") ALL(6, "PRMT") ALL(8, "IMAD.HI")
+  ALL(0, "IDP.2A") ALL(7, "IDP.2A.S8") ALL(1, "IDP.4A") ALL(2, "IMAD") ALL(3, "IADD") ALL(4, "I2FP") ALL(5, "FFMA.RM") ALL(6, "PRMT") ALL(8, "IMAD.HI") ALL(9, "LOP3") ALL(10, "SHF") ALL(11, "FADD") ALL(12, "I2F.U16") ALL(13, "F2I") ALL(14, "POPC") ALL(15, "MUFU.RCP")
+  ALL(16, "vadd2") ALL(17, "IMNMX")
   return 0;
 }
